@@ -1,0 +1,101 @@
+/* pih.h - C ABI of the B200-native batched simulator that replaces peg-in-hole-gym's vectorised env.step.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Each entry
+ * point names the reference interface it replaces (paths relative to the reference repository).  The Python
+ * host (peg_in_hole_gym_b200/envs/*.py) binds these with ctypes and mirrors the reference's gym surface;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * All device pointers are CUDA device pointers on the handle's device; `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream).  Calls are asynchronous on that stream unless stated; a handle is not
+ * thread-safe; one handle per GPU / rank.  Every function returns 0 on success, <0 on error
+ * (see pih_last_error).  There is NO CPU fallback: without a CUDA device pih_create fails.
+ */
+#ifndef PIH_H
+#define PIH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIH_ABI_VERSION 1
+
+/* error codes */
+#define PIH_OK 0
+#define PIH_ERR_INVALID (-1)   /* bad argument / config (reference: assert in BaseEnv.__init__, base_env.py:16-17) */
+#define PIH_ERR_CUDA (-2)      /* CUDA runtime error or no device */
+#define PIH_ERR_STATE (-3)     /* step before reset (reference: AttributeError, base_env_mp.py:42) */
+
+/* Construction arguments: the kwargs of gym.make('peg-in-hole-mp-v0', client, task, mp_num, sub_num, offset,
+ * args, is_test) (README.md:38, base_env_mp.py:15, base_env.py:15) plus the NEW knobs of SURVEY.md Appendix D. */
+typedef struct pih_config {
+  int32_t task;             /* 0 'peg-in-hole' (base_env.py:9-11), 1 'random-fly' (README.md:38) */
+  int32_t arm;              /* 0 panda (utils.py:30-38), 1 ur5 (utils.py:40-48) */
+  int32_t fly_object;       /* args[0]: 0 'Banana', 1 'Amicelli' (README.md:38) */
+  int32_t num_envs;         /* envs resident on this device = local mp_num * sub_num */
+  int32_t sub_num;          /* envs per reference client; period of the offset layout (base_env.py:35-55) */
+  int32_t env_id_base;      /* global id of local env 0 (rank sharding; RNG is keyed by global id) */
+  float offset[3];          /* base_env.py:15 offset */
+  float dt;                 /* 1/240 (peg_in_hole.py:254) or args[1] (README.md:38) */
+  int32_t solver_iters;     /* Bullet numSolverIterations, default 50 */
+  int32_t ik_iters;         /* calculateInverseKinematics maxNumIterations, default 20 */
+  int32_t max_steps;        /* NEW time limit per episode, 0 = none (reference has none) */
+  int32_t auto_reset;       /* NEW 0 = reference behaviour (done envs frozen until reset, base_env.py:61-71) */
+  int32_t action_frame_env; /* NEW 0 = reference (actions are absolute world coordinates), 1 = relative to env origin */
+  int32_t device;           /* CUDA device ordinal */
+  uint64_t seed;            /* Philox key (reference: unseeded global MT19937, peg_in_hole.py:239) */
+} pih_config;
+
+typedef struct pih_handle pih_handle;
+
+/* ABI / layout queries */
+int pih_abi_version(void);
+int pih_state_words(void);                 /* 32-bit words of state per env (= 4 * float4 slots) */
+int pih_action_dim(int arm);               /* 4 panda (peg_in_hole.py:12), 6 ur5 (utils.py:70-72) */
+int pih_obs_dim(void);                     /* 5 (peg_in_hole.py:13) */
+
+/* BaseEnvMp.__init__ / BaseEnv.__init__ (base_env_mp.py:15-37, base_env.py:15-33).  `state_dev` is a caller-owned
+ * (torch-owned) device buffer of pih_state_words()*num_envs 32-bit words, laid out [slot][env][4] (float4 SoA). */
+int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out);
+/* BaseEnv.close (base_env.py:97-98) */
+void pih_destroy(pih_handle* h);
+const char* pih_last_error(const pih_handle* h);
+
+/* Env placement, BaseEnv._create_env (base_env.py:35-55): writes the world offset of local env i to out[3]. Host only. */
+int pih_env_offset(const pih_config* cfg, int32_t local_env, float out[3]);
+
+/* BaseEnvMp.reset / BaseEnv.reset (base_env_mp.py:54-63, base_env.py:84-94).  mask_dev: nullable uint8[num_envs]
+ * (NULL = every env, the reference behaviour).  Writes the first observation when obs_dev != NULL. */
+int pih_reset(pih_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream);
+
+/* BaseEnvMp.step -> worker -> BaseEnv.step (base_env_mp.py:40-51,75-87, base_env.py:60-75): apply_action
+ * (panda_execute / ur_execute, utils.py:60-82), one stepSimulation, get_info.  action_dev float[num_envs][A];
+ * obs_dev float[num_envs][5]; reward_dev float[num_envs]; done_dev uint8[num_envs].  Envs that are done keep their
+ * previous outputs (base_env.py:61-71) unless auto_reset. */
+int pih_step(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream);
+
+/* Same call with HOST buffers: the reference-facing plugin path (host lists in, host lists out).  Stages through
+ * pinned memory, H2D, step, D2H, and synchronises the stream before returning. */
+int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host, void* stream);
+
+/* Benchmark / synthetic rollouts: `steps` consecutive env.steps in ONE launch with actions
+ * action_space.sample() ~ U[-1,1]^A (README.md:48) drawn in-kernel from Philox (seed; env, global step).
+ * Outputs of the LAST step are written (nullable).  counters_dev: nullable uint64[2] += {env-steps, episodes done}. */
+int pih_rollout(pih_handle* h, int32_t steps, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                unsigned long long* counters_dev, void* stream);
+
+/* apply_action only (panda_execute/ur_execute up to the IK result, utils.py:60-82): writes the joint position
+ * targets float[num_envs][9] without stepping.  Parity hook for SURVEY.md rows a9-a13. */
+int pih_ik_targets(pih_handle* h, const float* action_dev, float* qtarget_dev, void* stream);
+
+/* getLinkState(ee)[0:2] for every env (utils.py:62-63): pos float[num_envs][3] (world), rot float[num_envs][9]. */
+int pih_ee_pose(pih_handle* h, float* pos_dev, float* rot_dev, void* stream);
+
+/* FP32 FMA-throughput micro-benchmark (roofline denominator): returns measured TFLOP/s. */
+int pih_measure_fp32_peak(int device, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

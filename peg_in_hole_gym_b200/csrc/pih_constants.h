@@ -1,0 +1,86 @@
+/* Physics / scene constants (DATA only) shared by the CPU oracle and the CUDA kernels.
+ * Every value cites the reference line it restates (paths relative to the reference repo) or is
+ * marked NEW (reference silent; defined in DESIGN.md) / [3P] (PyBullet default, unverified here). */
+#ifndef PIH_CONSTANTS_H
+#define PIH_CONSTANTS_H
+
+#define PIH_NB_MAX 9            /* panda: 7 arm + 2 fingers; ur5: 6 */
+#define PIH_MAXC 8              /* contact points kept per env per step (deepest-first) */
+#define PIH_STATE_F4 10         /* float4 slots of env state (layout: DESIGN.md section 4) */
+#define PIH_STATE_WORDS (4 * PIH_STATE_F4)
+
+/* state word indices inside the [PIH_STATE_F4][N][4] float4-SoA buffer */
+#define PIH_S_Q 0               /* 0..8   joint positions */
+#define PIH_S_STEP 9            /* int bits: steps taken in this episode */
+#define PIH_S_EPISODE 10        /* int bits: episode index (RNG counter) */
+#define PIH_S_FLAGS 11          /* int bits: bit0 done, bit1 success, bits 8..15 contact-pair mask */
+#define PIH_S_QD 12             /* 12..20 joint velocities */
+#define PIH_S_PPOS 24           /* 24..26 peg / free-body position (env frame) */
+#define PIH_S_PQUAT 27          /* 27..30 orientation quaternion x,y,z,w */
+#define PIH_S_PVEL 32           /* 32..34 linear velocity */
+#define PIH_S_PANG 35           /* 35..37 angular velocity (env frame) */
+
+#define PIH_FLAG_DONE 1
+#define PIH_FLAG_SUCCESS 2
+#define PIH_PAIR_SHIFT 8
+#define PIH_PAIR_PEG_TABLE 1    /* contact-pair presence bits (<< PIH_PAIR_SHIFT) */
+#define PIH_PAIR_PEG_HOLE 2
+#define PIH_PAIR_PEG_FINGER1 4
+#define PIH_PAIR_PEG_FINGER2 8
+#define PIH_PAIR_ARM_TABLE 16
+
+/* tasks / arms */
+#define PIH_TASK_PEG_IN_HOLE 0
+#define PIH_TASK_RANDOM_FLY 1
+#define PIH_ARM_PANDA 0
+#define PIH_ARM_UR5 1
+
+/* world */
+#define PIH_GRAVITY 9.8                 /* envs/peg_in_hole.py:230 gravity (0,0,-9.8) */
+#define PIH_DT_DEFAULT (1.0 / 240.0)    /* envs/peg_in_hole.py:254; Bullet default [3P] */
+#define PIH_SOLVER_ITERS 50             /* Bullet default numSolverIterations [3P] */
+#define PIH_ERP 0.2                     /* Bullet default erp / contact erp [3P] */
+#define PIH_CONTACT_MARGIN 0.002        /* NEW: contacts created when distance < margin */
+#define PIH_TABLE_Z (-0.05)             /* table top: base z -1.3 + 2*(0.6+0.025), envs/utils.py:24-28, peg_in_hole.py:235 */
+
+/* IK: calculateInverseKinematics defaults [3P] */
+#define PIH_IK_ITERS 20
+#define PIH_IK_RESIDUAL 1e-4
+#define PIH_IK_LAMBDA 0.6               /* BussIK DefaultDampingLambda as shipped in Bullet [3P] */
+#define PIH_IK_MAXANGLE 0.7853981633974483  /* 45 deg per-iteration clamp [3P] */
+#define PIH_DV (2.0 / 240.0)            /* envs/utils.py:60 panda_execute dv */
+
+/* peg: one rigid end segment of pipe.urdf (globalScaling 0.01): cylinder r=1,len=6 mesh units along local y
+ * (assets/urdf/pipe.urdf:29-35,53-54; envs/peg_in_hole.py:242); mass/inertia as Bullet box-of-AABB [3P] */
+#define PIH_PEG_R 0.01
+#define PIH_PEG_HL 0.03
+#define PIH_PEG_MASS 0.0111
+#define PIH_PEG_MU 100.0                /* pipe.urdf:10 lateral_friction */
+#define PIH_PEG_SPAWN_Z 0.11            /* envs/peg_in_hole.py:239 */
+/* hole: annular tube cylinder_base.obj scaled 0.016, yaw pi/2 => axis along env x (hole.urdf, peg_in_hole.py:248-251) */
+#define PIH_HOLE_X 0.5
+#define PIH_HOLE_Y (-0.2)
+#define PIH_HOLE_Z 0.2
+#define PIH_HOLE_RIN 0.01536
+#define PIH_HOLE_ROUT 0.0192
+#define PIH_HOLE_HL 0.016
+#define PIH_SUCCESS_RADIUS 0.05         /* envs/peg_in_hole.py:114 */
+#define PIH_MU_DEFAULT 0.5              /* Bullet default lateral friction [3P] */
+#define PIH_MU_FINGER 1.0               /* panda finger lateral_friction [3P] */
+
+/* random-fly free bodies (assets/urdf/banana.urdf:5-15; Amicelli_800_tex.urdf:5-15): mass 1, mu 0;
+ * collision = AABB box of the convex pieces */
+#define PIH_FLY_MASS 1.0
+#define PIH_FLY_MU 0.0
+#define PIH_BANANA_HX 0.09865
+#define PIH_BANANA_HY 0.0376
+#define PIH_BANANA_HZ 0.0187
+#define PIH_AMICELLI_HX 0.0225
+#define PIH_AMICELLI_HY 0.0212
+#define PIH_AMICELLI_HZ 0.037
+
+/* RNG stream ids (Philox4x32-10 counter word 2) */
+#define PIH_STREAM_RESET 0
+#define PIH_STREAM_ACTION 1
+
+#endif
