@@ -1,0 +1,313 @@
+#!/usr/bin/env python3
+"""bench.py - peg-in-hole env-steps/s on 1/2/4/8 B200 (BASELINE.json metric), beside the CPU restatement.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is ONE vectorised env.step (apply_action + one engine step + get_info, auto-reset when triggered) over the
+whole batch of sub-environments resident on a GPU: BASELINE config 2 = panda peg-in-hole, 4096 sub-envs per GPU,
+dt 1/240, 200-step episodes, actions ~ action_space.sample() = U[-1,1]^4 centred on each env's origin.
+
+value  : env-steps/s, whole job (all ranks), inputs (state + pre-generated action tensors) resident in HBM, one
+         pih_step launch per step, timed per step with CUDA events on the launching stream; L2 is flushed
+         (256 MiB memset) between timed steps; max over ranks of the summed device time.
+e2e    : same metric through the host-buffer plugin call (pih_step_host): numpy actions in pinned staging -> H2D ->
+         step -> D2H of (obs, reward, done) -> stream sync, every step, wall clock.
+roofline: FP32 CUDA-core pipe (binding) against an FMA-throughput probe measured in the same run, plus
+         the HBM line (algorithmic state bytes / kernel time against MEASURED_PEAKS.json hbm_gbs).
+cpu_baseline: the CPU oracle (oracle/, float build; "CPU restatement - not PyBullet") on the host cores, bounded sample.
+
+--impl reference: PyBullet is not installable here (no wheel, no network), so the reference arm times the oracle port
+with all host threads on the same config, as the tier contract prescribes.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+ENVS_PER_GPU = 4096
+MAX_STEPS = 200
+OFFSET = (2.0, 3.0, 0.0)   # README.md:38
+SEED = 0
+# algorithmic cost per env-step (SURVEY.md 8d formula)
+BYTES_PER_ENV_STEP = 2 * 160 + 16 + 20 + 4 + 1   # float4-SoA state read+write (10 slots), action, obs, reward, done
+FLOPS_BULLET_DEFAULT = 2.2e5                       # I_ik=20, I_pgs=50, n=9, R=33
+
+
+def flops_per_env_step(n=9, na=7, i_ik=20, i_pgs=50, rows=17):
+    """SURVEY.md 8(d) formula with the parameters this build runs (R = 9 motors + 2 finger limits + 2 contacts x 3)."""
+    return 70 * n + i_ik * (174 * na + 200) + 430 * n + 250 * n * rows + 70 * rows * i_pgs + 2500
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(n_envs, steps, threads):
+    """env-steps/s of the CPU oracle (float build) on `threads` host threads: bounded sample of the same workload."""
+    import oracle_lib as ol
+    cfg = ol.make_config(n_envs, offset=OFFSET, seed=SEED, max_steps=MAX_STEPS, auto_reset=1)
+    o = ol.Oracle(cfg)
+    o.reset()
+    L = ol.lib()
+
+    def work(lo, hi):
+        L.pih_oracle_rollout_range(o.h, steps, lo, hi, None, None, None, None)
+    ths = [threading.Thread(target=work, args=(i * n_envs // threads, (i + 1) * n_envs // threads)) for i in range(threads)]
+    t0 = time.perf_counter()
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    dt = time.perf_counter() - t0
+    L.pih_oracle_advance_global_step(o.h, steps)
+    return n_envs * steps / dt, dt
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation is PyBullet (not installable here) -> oracle port."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = host_threads()
+    # one bench "step" = one env.step of the sample batch; sample sized for a few seconds per step-block
+    n = max(threads * 8, 64)
+    block = 25
+    import oracle_lib as ol
+    ol.lib()
+    for _ in range(max(args.warmup // block, 1)):
+        cpu_oracle_rate(n, block, threads)
+    t_steps = max(args.steps // block, 1) * block
+    rate, dt = cpu_oracle_rate(n, t_steps, threads)
+    line = {"impl": "reference", "metric": "peg-in-hole env-steps/sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / t_steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "peg-in-hole panda, dt 1/240, 200-step episodes, U[-1,1]^4 actions (config 2 shape)",
+                       "envs": n, "note": "PyBullet not installable (no wheel/network): CPU restatement (oracle/), not PyBullet"},
+            "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} envs x {t_steps} steps, {threads} host threads"},
+            "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--arm", default="panda")
+    ap.add_argument("--task", default="peg-in-hole")
+    ap.add_argument("--gather", action="store_true", help="all ranks send packed (obs,reward,done) rows to rank 0 every step (NCCL)")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps (diagnostic)")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from peg_in_hole_gym_b200 import _native
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    from peg_in_hole_gym_b200.parallel import gather_rows_to_rank0, pack_rows
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs_per_gpu
+    adim = 4 if args.arm == "panda" else 6
+    dt_sim = 1.0 / 120.0 if args.task == "random-fly" else 1.0 / 240.0
+    sim = BatchedSim(n, task=args.task, arm=args.arm, sub_num=n, env_id_base=rank * n, offset=OFFSET, dt=dt_sim, seed=SEED,
+                     max_steps=MAX_STEPS, auto_reset=True, device=local)
+    sim.reset()
+    # synthetic actions resident in HBM: U[-1,1]^A centred on each env origin, a ring of 64 pre-generated batches
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    offs = sim.env_offsets().to(dev)
+    ring = []
+    for _ in range(64):
+        a = torch.rand(n, adim, device=dev, generator=g) * 2 - 1
+        a[:, :3] += offs
+        ring.append(a.contiguous())
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    L = _native.lib()
+    peak_tf = None
+    if rank == 0:
+        import ctypes as C
+        v = C.c_double()
+        if L.pih_measure_fp32_peak(local, C.byref(v)) == 0:
+            peak_tf = v.value
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one(i, timed):
+        if flush is not None:
+            flush.zero_()
+        if timed is not None:
+            timed[0].record()
+        sim.step(ring[i % len(ring)])
+        if args.gather and world > 1:
+            gather_rows_to_rank0(pack_rows(sim.obs, sim.reward, sim.done.float()), counts=[n] * world)
+        if timed is not None:
+            timed[1].record()
+
+    for i in range(max(args.warmup, 3)):
+        one(i, None)
+    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        one(i, evs[i])
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop() if sampler else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # back-to-back K steps without flush, bracketed by one event pair (launch gaps included) - reported as extra
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        sim.step(ring[i % len(ring)])
+    e1.record()
+    barrier()
+    b2b_ms = e0.elapsed_time(e1)
+    # single-launch rollout (in-kernel Philox actions)
+    e0.record()
+    sim.rollout(args.steps, count=False)
+    e1.record()
+    barrier()
+    roll_ms = e0.elapsed_time(e1)
+    # e2e: host buffers through pih_step_host
+    h_ring = [r.cpu().numpy() for r in ring[:8]]
+    obs_h, rew_h, done_h = np.zeros((n, 5), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    e2e_steps = min(args.steps, 400)
+    for i in range(5):
+        sim.step_host(h_ring[i % 8], obs_h, rew_h, done_h)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        sim.step_host(h_ring[i % 8], obs_h, rew_h, done_h)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    dev_ms, b2b_ms, roll_ms, e2e_s = reduce_max(dev_ms), reduce_max(b2b_ms), reduce_max(roll_ms), reduce_max(e2e_s)
+    if rank == 0:
+        total_envs = n * world
+        value = total_envs * args.steps / (dev_ms * 1e-3)
+        kern_s = dev_ms * 1e-3 / args.steps
+        f_run = flops_per_env_step()
+        ach_tf = f_run * n / kern_s / 1e12
+        peaks = measured_peaks()
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        ach_gbs = BYTES_PER_ENV_STEP * n / kern_s / 1e9
+        cpu = None
+        if not args.no_cpu and world == 1:
+            thr = host_threads()
+            cn = max(thr * 8, 64)
+            cpu_oracle_rate(cn, 10, thr)
+            cst = 100
+            crate, cdt = cpu_oracle_rate(cn, cst, thr)
+            if cdt < 5.0:
+                cst = int(min(4000, cst * 10.0 / max(cdt, 1e-3)))
+                crate, cdt = cpu_oracle_rate(cn, cst, thr)
+            cpu = {"value": crate, "unit": "env-steps/s", "cores": thr, "kind": "port",
+                   "sample": f"CPU restatement (oracle/, not PyBullet): {cn} envs x {cst} steps of the same workload on {thr} host threads, {cdt:.1f} s"}
+        line = {
+            "metric": "peg-in-hole env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.task} {args.arm}, {n} sub-envs per GPU (BASELINE config 2), dt 1/{round(1 / dt_sim)}, "
+                                   f"{MAX_STEPS}-step episodes + auto-reset, U[-1,1]^{adim} actions centred on env origin, offset {list(OFFSET)}",
+                       "envs_per_gpu": n, "total_envs": total_envs, "solver_iters": 50, "ik_iters": 20,
+                       "l2": "not flushed" if args.no_flush else "flushed between timed steps (256 MiB memset); per-step CUDA events summed",
+                       "gather_to_rank0": bool(args.gather), "parallelism": f"env-sharded x{world}, no data-path collective"},
+            "e2e": {"value": total_envs * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * adim * 4,
+                    "d2h_bytes_per_step": n * (20 + 4 + 1), "steps": e2e_steps, "timing": "wall clock incl. pinned staging + H2D + step + D2H + sync"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": (ach_tf / peak_tf) if peak_tf else None, "traffic": None,
+                         "peak_source": "in-run FFMA probe (pih_measure_fp32_peak); FP32 pipe is not in MEASURED_PEAKS.json",
+                         "flops_per_env_step": f_run, "flops_per_env_step_bullet_default": FLOPS_BULLET_DEFAULT,
+                         "kernel": "pih::k_step<panda>", "kernel_us": kern_s * 1e6,
+                         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                                 "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"}},
+            "cpu_baseline": cpu,
+            "extra": {"back_to_back_value": total_envs * args.steps / (b2b_ms * 1e-3), "rollout_single_launch_value": total_envs * args.steps / (roll_ms * 1e-3),
+                      "wall_s_timed_region": t_wall},
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -853,6 +853,13 @@ static inline void FN(plane_space)(v3 n, v3* t1, v3* t2) {
   }
 }
 
+/* clamp |v| to PIH_MAX_COORD_VEL (btMultiBody m_maxCoordinateVelocity [3P]) */
+static inline v3 FN(clamp_norm)(v3 v) {
+  real n2 = FN(v3_dot)(v, v);
+  if (n2 > RC(PIH_MAX_COORD_VEL * PIH_MAX_COORD_VEL)) return FN(v3_scale)(v, RC(PIH_MAX_COORD_VEL) / SQRT(n2));
+  return v;
+}
+
 /* ------------------------------------------------------------------ one env.step */
 typedef struct {
   int has_fb, arm_body;
@@ -969,7 +976,7 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
     v3 Iw = FN(v3_make)(M->fb_idiag.x * wb.x, M->fb_idiag.y * wb.y, M->fb_idiag.z * wb.z);
     v3 g = FN(v3_cross)(wb, Iw);
     v3 al = FN(v3_make)(-(g.x * M->fb_iinv.x), -(g.y * M->fb_iinv.y), -(g.z * M->fb_iinv.z));
-    fw = FN(v3_axpy)(dt, FN(m3_v)(&Rfb, al), fw);
+    fw = FN(clamp_norm)(FN(v3_axpy)(dt, FN(m3_v)(&Rfb, al), fw));
   }
   /* world inverse inertia  Rfb diag(iinv) Rfb^T */
   m3 Iinv;
@@ -982,29 +989,29 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
   /* ---- constraint rows ---- */
   /* motors: POSITION_CONTROL, v* = kp (q*-q)/dt (kd=1, target velocity 0), |impulse| <= maxForce dt */
   real m_dinv[NBM], m_b[NBM], m_lam[NBM], m_max[NBM];
-  int l_sgn[NBM];
-  real l_b[NBM], l_lam[NBM];
+  int l_on[2][NBM];            /* [0] lower, [1] upper */
+  real l_b[2][NBM], l_lam[2][NBM];
   const real idt = RC(1) / dt;
   for (int j = 0; j < nb; ++j) {
-    real vstar = M->kp[j] * (qstar[j] - S->q[j]) * idt;
+    /* position targets outside the URDF limits are unreachable: the motor aims at the
+     * limit instead of fighting the limit row with its 1e5 N force cap (NEW, keeps PGS well conditioned) */
+    real qt = qstar[j];
+    qt = (qt < M->lo[j]) ? M->lo[j] : ((qt > M->hi[j]) ? M->hi[j] : qt);
+    real vstar = M->kp[j] * (qt - S->q[j]) * idt;
     m_dinv[j] = RC(1) / Minv[j][j];
     m_b[j] = (vstar - vs[j]) * m_dinv[j];
     m_lam[j] = RC(0);
     m_max[j] = M->maxf[j] * dt;
-    /* joint limits (btMultiBodyJointLimitConstraint [3P]): a row exists when the limit is reachable this step:
+    /* joint limits (btMultiBodyJointLimitConstraint [3P]): a row exists for each limit that is reachable this step:
      * gap < |v*| dt + |v| dt + 0.02 ; inside the limit the joint may close the gap, outside it is pushed back with ERP */
     real reachv = FMA(ABS(vstar) + ABS(S->qd[j]), dt, RC(0.02));
     real glo = S->q[j] - M->lo[j], ghi = M->hi[j] - S->q[j];
-    l_sgn[j] = 0; l_b[j] = RC(0); l_lam[j] = RC(0);
-    if (glo < reachv && glo <= ghi) {
-      l_sgn[j] = 1;
-      real tv = (glo > RC(0)) ? -(glo * idt) : -(RC(PIH_ERP) * glo * idt);
-      l_b[j] = (tv - vs[j]) * m_dinv[j];
-    } else if (ghi < reachv) {
-      l_sgn[j] = -1;
-      real tv = (ghi > RC(0)) ? -(ghi * idt) : -(RC(PIH_ERP) * ghi * idt);
-      l_b[j] = (tv + vs[j]) * m_dinv[j];
-    }
+    l_on[0][j] = glo < reachv; l_on[1][j] = ghi < reachv;
+    l_lam[0][j] = l_lam[1][j] = RC(0);
+    real tlo = (glo > RC(0)) ? -(glo * idt) : -(RC(PIH_ERP) * glo * idt);
+    real thi = (ghi > RC(0)) ? -(ghi * idt) : -(RC(PIH_ERP) * ghi * idt);
+    l_b[0][j] = (tlo - vs[j]) * m_dinv[j];
+    l_b[1][j] = (thi + vs[j]) * m_dinv[j];
   }
   /* contacts */
   contactset CS;
@@ -1071,16 +1078,17 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
       m_lam[j] = s;
       for (int i = 0; i < nb; ++i) dva[i] = FMA(Minv[i][j], dl, dva[i]);
     }
-    for (int j = 0; j < nb; ++j) {
-      if (!l_sgn[j]) continue;
-      real sg = (real)l_sgn[j];
-      real dl = FMA(-(sg * dva[j]), m_dinv[j], l_b[j]);
-      real s = l_lam[j] + dl;
-      s = (s < RC(0)) ? RC(0) : s;
-      dl = (s - l_lam[j]) * sg;
-      l_lam[j] = s;
-      for (int i = 0; i < nb; ++i) dva[i] = FMA(Minv[i][j], dl, dva[i]);
-    }
+    for (int j = 0; j < nb; ++j)
+      for (int side = 0; side < 2; ++side) {
+        if (!l_on[side][j]) continue;
+        real sg = side ? RC(-1) : RC(1);
+        real dl = FMA(-(sg * dva[j]), m_dinv[j], l_b[side][j]);
+        real s = l_lam[side][j] + dl;
+        s = (s < RC(0)) ? RC(0) : s;
+        dl = (s - l_lam[side][j]) * sg;
+        l_lam[side][j] = s;
+        for (int i = 0; i < nb; ++i) dva[i] = FMA(Minv[i][j], dl, dva[i]);
+      }
     for (int pass = 0; pass < 2; ++pass)
       for (int k = 0; k < CS.n; ++k) {
         crow* r = &rows[k];
@@ -1108,11 +1116,13 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
   }
   /* ---- integrate (semi-implicit Euler) ---- */
   for (int j = 0; j < nb; ++j) {
-    S->qd[j] = vs[j] + dva[j];
+    real v = vs[j] + dva[j];
+    v = (v > RC(PIH_MAX_COORD_VEL)) ? RC(PIH_MAX_COORD_VEL) : ((v < RC(-PIH_MAX_COORD_VEL)) ? RC(-PIH_MAX_COORD_VEL) : v);
+    S->qd[j] = v;
     S->q[j] = FMA(dt, S->qd[j], S->q[j]);
   }
-  fv = FN(v3_add)(fv, dvl);
-  fw = FN(v3_add)(fw, dvw);
+  fv = FN(clamp_norm)(FN(v3_add)(fv, dvl));
+  fw = FN(clamp_norm)(FN(v3_add)(fw, dvw));
   S->pvel[0] = fv.x; S->pvel[1] = fv.y; S->pvel[2] = fv.z;
   S->pang[0] = fw.x; S->pang[1] = fw.y; S->pang[2] = fw.z;
   S->ppos[0] = FMA(dt, fv.x, S->ppos[0]); S->ppos[1] = FMA(dt, fv.y, S->ppos[1]); S->ppos[2] = FMA(dt, fv.z, S->ppos[2]);

@@ -41,6 +41,8 @@
 #define PIH_SOLVER_ITERS 50             /* Bullet default numSolverIterations [3P] */
 #define PIH_ERP 0.2                     /* Bullet default erp / contact erp [3P] */
 #define PIH_CONTACT_MARGIN 0.002        /* NEW: contacts created when distance < margin */
+#define PIH_MAX_COORD_VEL 100.0          /* btMultiBody m_maxCoordinateVelocity [3P]: clamp on joint rates, and on the
+                                           free body's |v| (m/s) and |w| (rad/s); keeps the explicit gyroscopic term bounded */
 #define PIH_TABLE_Z (-0.05)             /* table top: base z -1.3 + 2*(0.6+0.025), envs/utils.py:24-28, peg_in_hole.py:235 */
 
 /* IK: calculateInverseKinematics defaults [3P] */

@@ -1,0 +1,460 @@
+// pih_kernels.cu - kernels + C ABI (include/pih.h) of the B200-native batched peg-in-hole simulator.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -Xcompiler -fPIC -shared
+// There is NO CPU fallback in this library: every entry point drives a CUDA kernel or fails with PIH_ERR_CUDA.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "../../include/pih.h"
+#include "pih_step.cuh"
+
+namespace pih {
+
+
+// ------------------------------------------------------------------------------------------------ kernels
+// thread-per-env; grid = ceil(n / blockDim).  State is read once and written once per launch as float4 SoA.
+
+template <int ARM> __global__ void __launch_bounds__(128) k_reset(SimParams P, const unsigned char* __restrict__ mask, float* __restrict__ obs) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.n) return;
+  if (mask && !mask[e]) return;
+  EnvState S;
+  load_state(P, e, S);
+  S.episode += 1;
+  reset_env<ARM>(P, S, (unsigned)(P.env_id_base + e));
+  store_state(P, e, S);
+  if (obs) {
+    float o[5];
+    observe<ARM>(S, env_offset(P, e), o);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) obs[5 * (size_t)e + k] = o[k];
+  }
+}
+
+template <int ARM> __global__ void __launch_bounds__(128) k_step(SimParams P, const float* __restrict__ action, float* __restrict__ obs,
+                                                                float* __restrict__ reward, unsigned char* __restrict__ done) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.n) return;
+  constexpr int A = ArmDims<ARM>::ADIM;
+  EnvState S;
+  load_state(P, e, S);
+  float a[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  if (A == 4) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(action) + e);
+    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < A; ++k) a[k] = __ldg(&action[(size_t)A * e + k]);
+  }
+  float o[5], r;
+  unsigned char d;
+  if (!step_env<ARM>(P, S, a, env_offset(P, e), (unsigned)(P.env_id_base + e), o, r, d)) return;  // frozen: keep outputs
+  store_state(P, e, S);
+  if (obs) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) obs[5 * (size_t)e + k] = o[k];
+  }
+  if (reward) reward[e] = r;
+  if (done) done[e] = d;
+}
+
+template <int ARM> __global__ void __launch_bounds__(128) k_rollout(SimParams P, int steps, float* __restrict__ obs, float* __restrict__ reward,
+                                                                   unsigned char* __restrict__ done, unsigned long long* __restrict__ counters) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.n) return;
+  constexpr int A = ArmDims<ARM>::ADIM;
+  EnvState S;
+  load_state(P, e, S);
+  const v3 off = env_offset(P, e);
+  const unsigned gid = (unsigned)(P.env_id_base + e);
+  float o[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, r = 0.0f;
+  unsigned char d = 0;
+  bool any = false;
+  unsigned nsteps = 0, ndone = 0;
+  for (int t = 0; t < steps; ++t) {
+    float u[8], a[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    float u0[4];
+    rng4(P, gid, P.global_step + (unsigned)t, PIH_STREAM_ACTION, u0);
+    u[0] = u0[0]; u[1] = u0[1]; u[2] = u0[2]; u[3] = u0[3];
+    if (A > 4) { rng4(P, gid, P.global_step + (unsigned)t, PIH_STREAM_ACTION + 1, u0); u[4] = u0[0]; u[5] = u0[1]; u[6] = u0[2]; u[7] = u0[3]; }
+#pragma unroll
+    for (int k = 0; k < A; ++k) a[k] = fmaf(u[k], 2.0f, -1.0f);
+    if (!P.action_frame_env) { a[0] += off.x; a[1] += off.y; a[2] += off.z; }
+    float o2[5], r2;
+    unsigned char d2;
+    if (step_env<ARM>(P, S, a, off, gid, o2, r2, d2)) {
+      any = true;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) o[k] = o2[k];
+      r = r2; d = d2;
+      nsteps += 1; ndone += d2;
+    }
+  }
+  store_state(P, e, S);
+  if (any) {
+    if (obs) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) obs[5 * (size_t)e + k] = o[k];
+    }
+    if (reward) reward[e] = r;
+    if (done) done[e] = d;
+  }
+  if (counters) {
+    // warp-aggregated counters: one atomic pair per warp (reduction over the lanes that are still active)
+    const unsigned m = __activemask();
+    unsigned ws = __reduce_add_sync(m, nsteps), wd = __reduce_add_sync(m, ndone);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) { atomicAdd(&counters[0], (unsigned long long)ws); atomicAdd(&counters[1], (unsigned long long)wd); }
+  }
+}
+
+template <int ARM> __global__ void __launch_bounds__(128) k_ik(SimParams P, const float* __restrict__ action, float* __restrict__ qtarget) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.n) return;
+  constexpr int A = ArmDims<ARM>::ADIM, nb = ArmDims<ARM>::NB;
+  EnvState S;
+  load_state(P, e, S);
+  float a[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+  for (int k = 0; k < A; ++k) a[k] = action[(size_t)A * e + k];
+  FK<ARM> F;
+  fk<ARM, nb>(S.q, F);
+  float qs[nb];
+  apply_action<ARM>(P, S, F, a, env_offset(P, e), qs);
+#pragma unroll
+  for (int k = 0; k < PIH_NB_MAX; ++k) qtarget[(size_t)PIH_NB_MAX * e + k] = (k < nb) ? qs[k < nb ? k : 0] : 0.0f;
+}
+
+template <int ARM> __global__ void __launch_bounds__(128) k_ee(SimParams P, float* __restrict__ pos, float* __restrict__ rot) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.n) return;
+  constexpr int nb = ArmDims<ARM>::NB;
+  EnvState S;
+  load_state(P, e, S);
+  FK<ARM> F;
+  fk<ARM, nb>(S.q, F);
+  v3 pee; m3 Ree;
+  ee_pose<ARM>(F, pee, Ree);
+  v3 off = env_offset(P, e);
+  if (pos) { pos[3 * (size_t)e] = pee.x + off.x; pos[3 * (size_t)e + 1] = pee.y + off.y; pos[3 * (size_t)e + 2] = pee.z + off.z; }
+  if (rot) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) rot[9 * (size_t)e + i] = Ree.m[i / 3][i % 3];
+  }
+}
+
+__global__ void k_init_state(float4* state, int n) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  for (int s = 0; s < PIH_STATE_F4; ++s) state[(size_t)s * n + e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  // episode = -1 (no reset yet), identity quaternion
+  reinterpret_cast<float*>(&state[(size_t)(PIH_S_EPISODE >> 2) * n + e])[PIH_S_EPISODE & 3] = __int_as_float(-1);
+  reinterpret_cast<float*>(&state[(size_t)((PIH_S_PQUAT + 3) >> 2) * n + e])[(PIH_S_PQUAT + 3) & 3] = 1.0f;
+}
+
+// FP32 FMA throughput probe (roofline denominator): 8 independent FFMA chains per thread
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1.0f, x2 = x0 + 2.0f, x3 = x0 + 3.0f, x4 = x0 + 4.0f, x5 = x0 + 5.0f, x6 = x0 + 6.0f, x7 = x0 + 7.0f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 123.456f) out[0] = s;
+}
+
+}  // namespace pih
+
+// ------------------------------------------------------------------------------------------------ host side
+using namespace pih;
+
+struct pih_handle {
+  pih_config cfg;
+  SimParams P;
+  int was_reset;
+  int block;
+  char err[256];
+  // staging for pih_step_host
+  float *h_action, *h_obs, *h_reward;
+  unsigned char* h_done;
+  float *d_action, *d_obs, *d_reward;
+  unsigned char* d_done;
+};
+
+static int g_tables_device = -1;
+
+static int fail(pih_handle* h, int code, const char* what, cudaError_t ce) {
+  if (h) snprintf(h->err, sizeof(h->err), "%s%s%s", what, ce != cudaSuccess ? ": " : "", ce != cudaSuccess ? cudaGetErrorString(ce) : "");
+  return code;
+}
+
+#define FILL_ARM(T, P)                                                                          \
+  do {                                                                                          \
+    (T).nb = PIH_##P##_NB; (T).narm = PIH_##P##_NARM; (T).ee_body = PIH_##P##_EE_BODY;            \
+    (T).nsph = PIH_##P##_NSPH; (T).nbox = PIH_##P##_NBOX;                                       \
+    for (int i = 0; i < PIH_##P##_NB; ++i) {                                                    \
+      (T).parent[i] = PIH_##P##_PARENT[i]; (T).jtype[i] = PIH_##P##_JTYPE[i];                    \
+      unsigned a = 1u << i;                                                                     \
+      for (int p = PIH_##P##_PARENT[i]; p >= 0; p = PIH_##P##_PARENT[p]) a |= 1u << p;           \
+      (T).anc[i] = a;                                                                           \
+      for (int r = 0; r < 3; ++r) {                                                             \
+        for (int c = 0; c < 3; ++c) {                                                           \
+          (T).R0[i][r][c] = (float)PIH_##P##_R0[i][3 * r + c];                                   \
+          (T).Irot[i][r][c] = (float)PIH_##P##_IROT[i][3 * r + c];                               \
+        }                                                                                       \
+        (T).t0[i][r] = (float)PIH_##P##_T0[i][r]; (T).h[i][r] = (float)PIH_##P##_H[i][r];         \
+      }                                                                                         \
+      (T).mass[i] = (float)PIH_##P##_MASS[i]; (T).lo[i] = (float)PIH_##P##_LO[i]; (T).hi[i] = (float)PIH_##P##_HI[i]; \
+      (T).damp[i] = (float)PIH_##P##_DAMP[i]; (T).maxf[i] = (float)PIH_##P##_MAXF[i];            \
+      (T).kp[i] = (float)PIH_##P##_KP[i]; (T).rest[i] = (float)PIH_##P##_REST[i];                \
+    }                                                                                           \
+    for (int r = 0; r < 3; ++r) {                                                               \
+      for (int c = 0; c < 3; ++c) (T).ee_R[r][c] = (float)PIH_##P##_EE_R[3 * r + c];             \
+      (T).ee_t[r] = (float)PIH_##P##_EE_T[r];                                                   \
+    }                                                                                           \
+    for (int s = 0; s < PIH_MAX_SPH; ++s) {                                                     \
+      (T).sph_body[s] = PIH_##P##_SPH_BODY[s]; (T).sph_r[s] = (float)PIH_##P##_SPH_R[s];         \
+      for (int r = 0; r < 3; ++r) (T).sph_c[s][r] = (float)PIH_##P##_SPH_C[s][r];                \
+    }                                                                                           \
+    for (int s = 0; s < PIH_MAX_BOX; ++s) {                                                     \
+      (T).box_body[s] = PIH_##P##_BOX_BODY[s];                                                  \
+      for (int r = 0; r < 3; ++r) {                                                             \
+        (T).box_c[s][r] = (float)PIH_##P##_BOX_C[s][r]; (T).box_h[s][r] = (float)PIH_##P##_BOX_H[s][r]; \
+        for (int c = 0; c < 3; ++c) (T).box_R[s][r][c] = (float)PIH_##P##_BOX_R[s][3 * r + c];   \
+      }                                                                                         \
+    }                                                                                           \
+  } while (0)
+
+static cudaError_t upload_tables() {
+  static ArmTables host[2];
+  memset(host, 0, sizeof(host));
+  FILL_ARM(host[PIH_ARM_PANDA], PANDA);
+  FILL_ARM(host[PIH_ARM_UR5], UR5);
+  return cudaMemcpyToSymbol(c_arm, host, sizeof(host));
+}
+
+extern "C" {
+
+int pih_abi_version(void) { return PIH_ABI_VERSION; }
+int pih_state_words(void) { return PIH_STATE_WORDS; }
+int pih_action_dim(int arm) { return arm == PIH_ARM_PANDA ? 4 : (arm == PIH_ARM_UR5 ? 6 : PIH_ERR_INVALID); }
+int pih_obs_dim(void) { return 5; }
+
+int pih_env_offset(const pih_config* cfg, int32_t local_env, float out[3]) {
+  if (!cfg || !out) return PIH_ERR_INVALID;
+  int sub = cfg->sub_num > 0 ? cfg->sub_num : cfg->num_envs;
+  if (sub <= 0) return PIH_ERR_INVALID;
+  int e = (cfg->env_id_base + local_env) % sub;
+  if (cfg->offset[0] == 0.0f || cfg->offset[1] == 0.0f) {
+    out[0] = cfg->offset[0] * (float)e; out[1] = cfg->offset[1] * (float)e; out[2] = cfg->offset[2] * (float)e;
+  } else {
+    int s = 0;
+    while (s * s < sub) ++s;
+    out[0] = cfg->offset[0] * (float)(e / s); out[1] = cfg->offset[1] * (float)(e % s); out[2] = cfg->offset[2];
+  }
+  return PIH_OK;
+}
+
+int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
+  if (!cfg || !out || !state_dev) return PIH_ERR_INVALID;
+  *out = nullptr;
+  if (cfg->num_envs <= 0 || cfg->sub_num <= 0) return PIH_ERR_INVALID;
+  if (cfg->task != PIH_TASK_PEG_IN_HOLE && cfg->task != PIH_TASK_RANDOM_FLY) return PIH_ERR_INVALID;
+  if (cfg->arm != PIH_ARM_PANDA && cfg->arm != PIH_ARM_UR5) return PIH_ERR_INVALID;
+  if (!(cfg->dt > 0.0f) || cfg->solver_iters < 0 || cfg->ik_iters < 0) return PIH_ERR_INVALID;
+  // reference assert: task_num == 1 or offset != [0,0,0] (envs/base_env.py:17)
+  if (cfg->sub_num > 1 && cfg->offset[0] == 0.0f && cfg->offset[1] == 0.0f && cfg->offset[2] == 0.0f) return PIH_ERR_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) return PIH_ERR_CUDA;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return PIH_ERR_CUDA;
+  pih_handle* h = new (std::nothrow) pih_handle();
+  if (!h) return PIH_ERR_INVALID;
+  memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  if (g_tables_device != cfg->device) {
+    cudaError_t ce = upload_tables();
+    if (ce != cudaSuccess) { delete h; return PIH_ERR_CUDA; }
+    g_tables_device = cfg->device;
+  }
+  SimParams& P = h->P;
+  P.n = cfg->num_envs; P.task = cfg->task; P.arm = cfg->arm;
+  P.sub_num = cfg->sub_num;
+  P.line_layout = (cfg->offset[0] == 0.0f || cfg->offset[1] == 0.0f) ? 1 : 0;
+  int s = 0;
+  while (s * s < cfg->sub_num) ++s;
+  P.grid_side = s > 0 ? s : 1;
+  P.env_id_base = cfg->env_id_base;
+  for (int k = 0; k < 3; ++k) P.offset[k] = cfg->offset[k];
+  P.dt = cfg->dt; P.idt = 1.0f / cfg->dt;
+  P.solver_iters = cfg->solver_iters; P.ik_iters = cfg->ik_iters; P.max_steps = cfg->max_steps;
+  P.auto_reset = cfg->auto_reset; P.action_frame_env = cfg->action_frame_env;
+  P.seed_lo = (unsigned)cfg->seed; P.seed_hi = (unsigned)(cfg->seed >> 32);
+  P.global_step = 0;
+  double hx, hy, hz, mass, mu;
+  if (cfg->task == PIH_TASK_RANDOM_FLY) {
+    P.fb_shape = 1;
+    if (cfg->fly_object == 0) { hx = PIH_BANANA_HX; hy = PIH_BANANA_HY; hz = PIH_BANANA_HZ; }
+    else { hx = PIH_AMICELLI_HX; hy = PIH_AMICELLI_HY; hz = PIH_AMICELLI_HZ; }
+    mass = PIH_FLY_MASS; mu = PIH_FLY_MU;
+  } else {
+    P.fb_shape = 0; hx = PIH_PEG_R; hy = PIH_PEG_HL; hz = PIH_PEG_R; mass = PIH_PEG_MASS; mu = PIH_PEG_MU;
+  }
+  double lx = 2 * (hx + 0.001), ly = 2 * (hy + 0.001), lz = 2 * (hz + 0.001);
+  double ix = mass / 12.0 * (ly * ly + lz * lz), iy = mass / 12.0 * (lx * lx + lz * lz), iz = mass / 12.0 * (lx * lx + ly * ly);
+  P.fb_mass = (float)mass; P.fb_im = 1.0f / P.fb_mass; P.fb_mu = (float)mu;
+  P.fb_half[0] = (float)hx; P.fb_half[1] = (float)hy; P.fb_half[2] = (float)hz;
+  P.fb_idiag[0] = (float)ix; P.fb_idiag[1] = (float)iy; P.fb_idiag[2] = (float)iz;
+  P.fb_iinv[0] = (float)(1.0 / ix); P.fb_iinv[1] = (float)(1.0 / iy); P.fb_iinv[2] = (float)(1.0 / iz);
+  P.state = reinterpret_cast<float4*>(state_dev);
+  h->block = 32;
+  const char* bs = getenv("PIH_BLOCK");
+  if (bs) { int b = atoi(bs); if (b == 32 || b == 64 || b == 128) h->block = b; }
+  k_init_state<<<(P.n + 127) / 128, 128>>>(P.state, P.n);
+  cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+  if (ce != cudaSuccess) { delete h; return PIH_ERR_CUDA; }
+  *out = h;
+  return PIH_OK;
+}
+
+void pih_destroy(pih_handle* h) {
+  if (!h) return;
+  if (h->h_action) cudaFreeHost(h->h_action);
+  if (h->h_obs) cudaFreeHost(h->h_obs);
+  if (h->h_reward) cudaFreeHost(h->h_reward);
+  if (h->h_done) cudaFreeHost(h->h_done);
+  if (h->d_action) cudaFree(h->d_action);
+  if (h->d_obs) cudaFree(h->d_obs);
+  if (h->d_reward) cudaFree(h->d_reward);
+  if (h->d_done) cudaFree(h->d_done);
+  delete h;
+}
+
+const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null handle"; }
+
+#define LAUNCH(kern, h, st, ...)                                                               \
+  do {                                                                                         \
+    int grid_ = ((h)->P.n + (h)->block - 1) / (h)->block;                                      \
+    if ((h)->P.arm == PIH_ARM_PANDA) kern<PIH_ARM_PANDA><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
+    else kern<PIH_ARM_UR5><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__);          \
+  } while (0)
+
+int pih_reset(pih_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+  if (!h) return PIH_ERR_INVALID;
+  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, PIH_ERR_CUDA, "cudaSetDevice", cudaGetLastError());
+  LAUNCH(k_reset, h, stream, h->P, mask_dev, obs_dev);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_reset launch", ce);
+  h->was_reset = 1;
+  return PIH_OK;
+}
+
+int pih_step(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream) {
+  if (!h || !action_dev) return PIH_ERR_INVALID;
+  if (!h->was_reset) return fail(h, PIH_ERR_STATE, "step() before reset()", cudaSuccess);
+  LAUNCH(k_step, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_step launch", ce);
+  h->P.global_step += 1;
+  return PIH_OK;
+}
+
+static int ensure_staging(pih_handle* h) {
+  if (h->h_action) return PIH_OK;
+  size_t n = (size_t)h->P.n;
+  cudaError_t ce = cudaMallocHost(&h->h_action, n * 6 * sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMallocHost(&h->h_obs, n * 5 * sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMallocHost(&h->h_reward, n * sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMallocHost(&h->h_done, n);
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_action, n * 6 * sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_obs, n * 5 * sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_reward, n * sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_done, n);
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_obs, 0, n * 5 * sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_reward, 0, n * sizeof(float));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_done, 0, n);
+  if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "staging allocation", ce);
+  return PIH_OK;
+}
+
+int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host, void* stream) {
+  if (!h || !action_host) return PIH_ERR_INVALID;
+  if (!h->was_reset) return fail(h, PIH_ERR_STATE, "step() before reset()", cudaSuccess);
+  int rc = ensure_staging(h);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n = (size_t)h->P.n, A = (size_t)pih_action_dim(h->P.arm);
+  memcpy(h->h_action, action_host, n * A * sizeof(float));
+  cudaError_t ce = cudaMemcpyAsync(h->d_action, h->h_action, n * A * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "H2D", ce);
+  rc = pih_step(h, h->d_action, h->d_obs, h->d_reward, h->d_done, stream);
+  if (rc) return rc;
+  ce = cudaMemcpyAsync(h->h_obs, h->d_obs, n * 5 * sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->h_reward, h->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "D2H", ce);
+  if (obs_host) memcpy(obs_host, h->h_obs, n * 5 * sizeof(float));
+  if (reward_host) memcpy(reward_host, h->h_reward, n * sizeof(float));
+  if (done_host) memcpy(done_host, h->h_done, n);
+  return PIH_OK;
+}
+
+int pih_rollout(pih_handle* h, int32_t steps, float* obs_dev, float* reward_dev, uint8_t* done_dev, unsigned long long* counters_dev, void* stream) {
+  if (!h || steps < 0) return PIH_ERR_INVALID;
+  if (!h->was_reset) return fail(h, PIH_ERR_STATE, "rollout() before reset()", cudaSuccess);
+  LAUNCH(k_rollout, h, stream, h->P, (int)steps, obs_dev, reward_dev, done_dev, counters_dev);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_rollout launch", ce);
+  h->P.global_step += (unsigned)steps;
+  return PIH_OK;
+}
+
+int pih_ik_targets(pih_handle* h, const float* action_dev, float* qtarget_dev, void* stream) {
+  if (!h || !action_dev || !qtarget_dev) return PIH_ERR_INVALID;
+  LAUNCH(k_ik, h, stream, h->P, action_dev, qtarget_dev);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_ik launch", ce);
+  return PIH_OK;
+}
+
+int pih_ee_pose(pih_handle* h, float* pos_dev, float* rot_dev, void* stream) {
+  if (!h) return PIH_ERR_INVALID;
+  LAUNCH(k_ee, h, stream, h->P, pos_dev, rot_dev);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_ee launch", ce);
+  return PIH_OK;
+}
+
+int pih_measure_fp32_peak(int device, double* tflops_out) {
+  if (!tflops_out) return PIH_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return PIH_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PIH_ERR_CUDA;
+  float* d_out = nullptr;
+  if (cudaMalloc(&d_out, 4) != cudaSuccess) return PIH_ERR_CUDA;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    k_fma_peak<<<blocks, threads>>>(d_out, iters, 1.0000001f, 1e-9f);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d_out); return PIH_ERR_CUDA; }
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double flops = 2.0 * (double)blocks * threads * (double)iters * 16.0 * 8.0;
+    double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops_out = best;
+  return PIH_OK;
+}
+
+}  // extern "C"

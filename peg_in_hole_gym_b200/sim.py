@@ -1,0 +1,120 @@
+"""BatchedSim - thin torch-side owner of the HBM-resident env state around the C ABI (include/pih.h).
+
+This is the layer that replaces L4+L3+L1+L0 of the reference: the multiprocessing fan-out
+(envs/base_env_mp.py:27-51), the per-sub-env Python loops (envs/base_env.py:60-71) and the PyBullet calls.  PyTorch
+is used for device memory and streams only; all arithmetic runs in the hand-written sm_100a kernels.
+"""
+import ctypes as C
+
+import torch
+
+from . import _native as N
+
+
+class BatchedSim:
+    """num_envs sub-environments resident on one GPU.  State lives in a torch-owned float4-SoA tensor
+    ``state[10, N, 4]`` (layout: csrc/pih_constants.h); outputs in ``obs[N,5]``, ``reward[N]``, ``done[N]``."""
+
+    def __init__(self, num_envs, task="peg-in-hole", arm="panda", fly_object="banana", sub_num=None, env_id_base=0,
+                 offset=(0.0, 0.0, 0.0), dt=1.0 / 240.0, solver_iters=50, ik_iters=20, max_steps=0, auto_reset=False,
+                 action_frame_env=False, device=None, seed=0):
+        L = N.lib()
+        if not torch.cuda.is_available():
+            raise N.PihError("peg_in_hole_gym_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
+        self.cfg = N.make_config(num_envs, task, arm, fly_object, sub_num, env_id_base, offset, dt, solver_iters,
+                                 ik_iters, max_steps, auto_reset, action_frame_env, self.device.index, seed)
+        self.n = int(num_envs)
+        self.action_dim = L.pih_action_dim(self.cfg.arm)
+        self.obs_dim = L.pih_obs_dim()
+        with torch.cuda.device(self.device):
+            self.state = torch.zeros(N.STATE_F4, self.n, 4, dtype=torch.float32, device=self.device)
+            self.obs = torch.zeros(self.n, self.obs_dim, dtype=torch.float32, device=self.device)
+            self.reward = torch.zeros(self.n, dtype=torch.float32, device=self.device)
+            self.done = torch.zeros(self.n, dtype=torch.uint8, device=self.device)
+            self.counters = torch.zeros(2, dtype=torch.int64, device=self.device)
+            torch.cuda.synchronize(self.device)
+            h = C.c_void_p()
+            N.check(L.pih_create(C.byref(self.cfg), self.state.data_ptr(), C.byref(h)), None, "pih_create")
+        self._h = h
+        self._L = L
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.pih_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # -- reference API equivalents
+    def reset(self, mask=None):
+        """BaseEnv.reset (envs/base_env.py:84-94).  mask: optional uint8/bool tensor [N]; None resets every env."""
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            self.reward[m.bool()] = 0
+            self.done[m.bool()] = 0
+        else:
+            self.reward.zero_()
+            self.done.zero_()
+        N.check(self._L.pih_reset(self._h, m.data_ptr() if m is not None else None, self.obs.data_ptr(), self._stream()),
+                self._h, "pih_reset")
+        return self.obs
+
+    def step(self, action):
+        """BaseEnv.step (envs/base_env.py:60-75) for all envs in one launch.  action: float32 CUDA tensor [N, A]."""
+        a = action
+        if not (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float32 and a.is_contiguous()):
+            a = torch.as_tensor(a, dtype=torch.float32).to(self.device, non_blocking=True).contiguous()
+        if a.numel() != self.n * self.action_dim:
+            raise ValueError(f"action has {a.numel()} elements, expected {self.n}x{self.action_dim}")
+        N.check(self._L.pih_step(self._h, a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                                 self._stream()), self._h, "pih_step")
+        return self.obs, self.reward, self.done
+
+    def step_host(self, action_np, obs_np, reward_np, done_np):
+        """Host-buffer plugin call (pih_step_host): numpy in, numpy out, H2D/D2H inside."""
+        N.check(self._L.pih_step_host(self._h, action_np.ctypes.data, obs_np.ctypes.data, reward_np.ctypes.data,
+                                      done_np.ctypes.data, self._stream()), self._h, "pih_step_host")
+
+    def rollout(self, steps, count=True):
+        """`steps` env.steps in one launch with in-kernel U[-1,1] actions (action_space.sample(), README.md:48)."""
+        N.check(self._L.pih_rollout(self._h, int(steps), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                                    self.counters.data_ptr() if count else None, self._stream()), self._h, "pih_rollout")
+        return self.obs, self.reward, self.done
+
+    def ik_targets(self, action):
+        a = torch.as_tensor(action, dtype=torch.float32).to(self.device).contiguous()
+        out = torch.zeros(self.n, 9, dtype=torch.float32, device=self.device)
+        N.check(self._L.pih_ik_targets(self._h, a.data_ptr(), out.data_ptr(), self._stream()), self._h, "pih_ik_targets")
+        return out
+
+    def ee_pose(self):
+        pos = torch.zeros(self.n, 3, dtype=torch.float32, device=self.device)
+        rot = torch.zeros(self.n, 9, dtype=torch.float32, device=self.device)
+        N.check(self._L.pih_ee_pose(self._h, pos.data_ptr(), rot.data_ptr(), self._stream()), self._h, "pih_ee_pose")
+        return pos, rot.view(self.n, 3, 3)
+
+    # -- state views (SoA words -> [N, k]); copies, for tests / checkpointing
+    def words(self, first, count=1):
+        flat = self.state.permute(1, 0, 2).reshape(self.n, -1)
+        return flat[:, first:first + count]
+
+    def int_word(self, word):
+        return self.words(word, 1).contiguous().view(torch.int32)[:, 0]
+
+    def env_offsets(self):
+        out = torch.zeros(self.n, 3)
+        buf = (C.c_float * 3)()
+        for i in range(self.n):
+            self._L.pih_env_offset(C.byref(self.cfg), i, buf)
+            out[i] = torch.tensor(list(buf))
+        return out

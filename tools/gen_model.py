@@ -235,6 +235,8 @@ def emit_arm(f, P, m, n_arm, rest, kp, maxforce, max_sph, max_box):
     f.write(f"/* ---- {P}: {nb} moving bodies: " + ", ".join(b["name"] for b in B) + " ---- */\n")
     f.write(f"#define PIH_{P}_NB {nb}\n#define PIH_{P}_NARM {n_arm}\n#define PIH_{P}_EE_BODY {m['ee_body']}\n")
     f.write(f"#define PIH_{P}_NSPH {len(m['spheres'])}\n#define PIH_{P}_NBOX {len(m['boxes'])}\n")
+    f.write(f"#define PIH_{P}_PARENT_LIST " + ", ".join(str(b["parent"]) for b in B) + "\n")
+    f.write(f"#define PIH_{P}_JTYPE_LIST " + ", ".join(str(b["jtype"]) for b in B) + "\n")
     f.write(f"static const int PIH_{P}_PARENT[{nb}] = {{" + ", ".join(str(b["parent"]) for b in B) + "};\n")
     f.write(f"static const int PIH_{P}_JTYPE[{nb}] = {{" + ", ".join(str(b["jtype"]) for b in B) + "};\n")
     f.write(f"static const double PIH_{P}_R0[{nb}][9] = {{" + ",\n  ".join(fmt(b["R0"]) for b in B) + "};\n")
@@ -251,10 +253,12 @@ def emit_arm(f, P, m, n_arm, rest, kp, maxforce, max_sph, max_box):
     f.write(f"static const double PIH_{P}_EE_R[9] = " + fmt(m["ee_R"]) + ";\n")
     f.write(f"static const double PIH_{P}_EE_T[3] = " + fmt(m["ee_t"]) + ";\n")
     sp = m["spheres"] + [(0, np.zeros(3), 0.0)] * (max_sph - len(m["spheres"]))
+    f.write(f"#define PIH_{P}_SPH_BODY_LIST " + ", ".join(str(s[0]) for s in sp) + "\n")
     f.write(f"static const int PIH_{P}_SPH_BODY[{max_sph}] = {{" + ", ".join(str(s[0]) for s in sp) + "};\n")
     f.write(f"static const double PIH_{P}_SPH_C[{max_sph}][3] = {{" + ", ".join(fmt(s[1]) for s in sp) + "};\n")
     f.write(f"static const double PIH_{P}_SPH_R[{max_sph}] = " + fmt([s[2] for s in sp]) + ";\n")
     bx = m["boxes"] + [(0, np.zeros(3), np.eye(3), np.zeros(3))] * (max_box - len(m["boxes"]))
+    f.write(f"#define PIH_{P}_BOX_BODY_LIST " + ", ".join(str(s[0]) for s in bx) + "\n")
     f.write(f"static const int PIH_{P}_BOX_BODY[{max_box}] = {{" + ", ".join(str(s[0]) for s in bx) + "};\n")
     f.write(f"static const double PIH_{P}_BOX_C[{max_box}][3] = {{" + ", ".join(fmt(s[1]) for s in bx) + "};\n")
     f.write(f"static const double PIH_{P}_BOX_R[{max_box}][9] = {{" + ",\n  ".join(fmt(s[2]) for s in bx) + "};\n")
