@@ -249,3 +249,49 @@ def test_full_size_properties_4096_envs():
     assert (q[:, 7:] > -1e-3).all() and (q[:, 7:] < 0.041).all()           # finger limits hold
     assert (ol.state_int(st, 10) == 1).all() and (ol.state_int(st, 9) == 10).all()
     assert int(a.counters[0].item()) == n * 210
+
+
+@pytest.mark.parametrize("case", ["panda_peg", "ur5_peg", "panda_fly"])
+def test_cuda_path_reproduces_golden_fixtures(case):
+    """Committed fixtures (tests/golden/, generated by gen_golden.py from the oracle): CUDA path must match them."""
+    import os
+    from golden.gen_golden import CASES, N, STEPS
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", case + ".npz"))
+    kw = dict(CASES[case])
+    task = {0: "peg-in-hole", 1: "random-fly"}[kw.pop("task")]
+    arm = {0: "panda", 1: "ur5"}[kw.pop("arm")]
+    if "fly_object" in kw:
+        kw["fly_object"] = {0: "banana", 1: "amicelli"}[kw["fly_object"]]
+    kw["auto_reset"] = bool(kw["auto_reset"])
+    sim = _sim(N, task=task, arm=arm, **kw)
+    assert np.array_equal(sim.reset().cpu().numpy(), g["obs0"])
+    for t in range(STEPS):
+        obs, r, d = sim.step(torch.from_numpy(g["actions"][t]).cuda())
+        assert np.array_equal(d.cpu().numpy(), g["done"][t]) and np.array_equal(r.cpu().numpy(), g["reward"][t]), t
+        assert np.array_equal(obs.cpu().numpy(), g["obs"][t]), t
+    assert np.array_equal(sim.state.cpu().numpy(), g["state"])
+
+
+def test_gym_surface_end_to_end():
+    """README usage loop (README.md:33-50) through the registered id, nested-list and tensor containers."""
+    import peg_in_hole_gym_b200 as gym
+    env = gym.make('peg-in-hole-mp-v0', client=gym.GUI, task='peg-in-hole', mp_num=2, sub_num=3, offset=[2., 3., 0.],
+                   args=None, is_test=True, max_steps=5, seed=1, shard=False)
+    with pytest.raises(AttributeError):
+        env.step(env.action_space.sample())
+    obs = env.reset()
+    assert tuple(obs.shape) == (2, 3, 5)
+    for t in range(5):
+        obs, reward, done, info = env.step(env.action_space.sample())      # nested [mp][sub] lists of Box samples
+    assert tuple(obs.shape) == (2, 3, 5) and tuple(reward.shape) == (2, 3) and done.dtype == torch.bool
+    assert bool(done.all()) and info[1][2]["success"] is False
+    frozen = obs.clone()
+    obs2, _, _, _ = env.step(env.action_space.sample_array())
+    assert torch.equal(obs2, frozen)                                      # done envs keep their outputs
+    env.close()
+    env = gym.make('peg-in-hole-v0', client=gym.DIRECT, task='random-fly', task_num=4, offset=[2., 0., 0.],
+                   args=['Banana', 1 / 120.], as_lists=True)
+    obs = env.reset()
+    o, r, d, i = env.step(env.action_space.sample())
+    assert isinstance(o, list) and len(o) == 4 and len(o[0]) == 5 and isinstance(i[0], dict)
+    env.close()
