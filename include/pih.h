@@ -38,6 +38,8 @@ typedef struct pih_config {
   int32_t env_id_base;      /* global id of local env 0 (rank sharding; RNG is keyed by global id) */
   float offset[3];          /* base_env.py:15 offset */
   float dt;                 /* 1/240 (peg_in_hole.py:254) or args[1] (README.md:38) */
+  float solver_residual;    /* PyBullet solverResidualThreshold [3P], default 1e-7: PGS stops early once the largest squared
+                               velocity change of any row in an iteration is <= this; 0 = always run solver_iters */
   int32_t solver_iters;     /* Bullet numSolverIterations, default 50 */
   int32_t ik_iters;         /* calculateInverseKinematics maxNumIterations, default 20 */
   int32_t max_steps;        /* NEW time limit per episode, 0 = none (reference has none) */

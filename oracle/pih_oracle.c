@@ -9,6 +9,9 @@
 #include "../peg_in_hole_gym_b200/csrc/pih_constants.h"
 #include "../peg_in_hole_gym_b200/csrc/pih_model_data.h"
 
+/* diagnostics only (not thread-safe counters; approximate under threads) */
+unsigned long long pih_dbg_pgs_iters = 0, pih_dbg_pgs_steps = 0;
+
 #define REAL float
 #define SUFFIX _f
 #define REAL_IS_DOUBLE 0
@@ -37,6 +40,7 @@ typedef struct {
   envstate_d* sd;
   float* off; /* [n][3] */
   uint32_t global_step;
+  int* last_nc; /* contacts found by the last step of each env (diagnostics) */
 } oracle;
 
 /* BaseEnv._create_env (base_env.py:35-55): line layout offset*i when offset.x==0 or offset.y==0, otherwise a
@@ -61,15 +65,16 @@ void* pih_oracle_create(const pih_config* cfg, int use_double) {
   int n = cfg->num_envs;
   model_init_f(&o->mf, cfg->arm, cfg->task, cfg->fly_object);
   model_init_d(&o->md, cfg->arm, cfg->task, cfg->fly_object);
-  o->cf.task = cfg->task; o->cf.arm = cfg->arm; o->cf.fly_object = cfg->fly_object; o->cf.dt = cfg->dt;
+  o->cf.task = cfg->task; o->cf.arm = cfg->arm; o->cf.fly_object = cfg->fly_object; o->cf.dt = cfg->dt; o->cf.solver_residual = cfg->solver_residual;
   o->cf.solver_iters = cfg->solver_iters; o->cf.ik_iters = cfg->ik_iters; o->cf.max_steps = cfg->max_steps;
   o->cf.auto_reset = cfg->auto_reset; o->cf.action_frame_env = cfg->action_frame_env; o->cf.seed = cfg->seed;
-  o->cd.task = cfg->task; o->cd.arm = cfg->arm; o->cd.fly_object = cfg->fly_object; o->cd.dt = (double)cfg->dt;
+  o->cd.task = cfg->task; o->cd.arm = cfg->arm; o->cd.fly_object = cfg->fly_object; o->cd.dt = (double)cfg->dt; o->cd.solver_residual = (double)cfg->solver_residual;
   o->cd.solver_iters = cfg->solver_iters; o->cd.ik_iters = cfg->ik_iters; o->cd.max_steps = cfg->max_steps;
   o->cd.auto_reset = cfg->auto_reset; o->cd.action_frame_env = cfg->action_frame_env; o->cd.seed = cfg->seed;
   o->sf = (envstate_f*)calloc(n, sizeof(envstate_f));
   o->sd = (envstate_d*)calloc(n, sizeof(envstate_d));
   o->off = (float*)calloc(3 * n, sizeof(float));
+  o->last_nc = (int*)calloc(n, sizeof(int));
   for (int i = 0; i < n; ++i) {
     pih_oracle_env_offset(cfg, i, &o->off[3 * i]);
     o->sf[i].episode = -1; o->sd[i].episode = -1;
@@ -81,7 +86,7 @@ void* pih_oracle_create(const pih_config* cfg, int use_double) {
 void pih_oracle_destroy(void* h) {
   oracle* o = (oracle*)h;
   if (!o) return;
-  free(o->sf); free(o->sd); free(o->off); free(o);
+  free(o->sf); free(o->sd); free(o->off); free(o->last_nc); free(o);
 }
 
 int pih_oracle_reset(void* h, const uint8_t* mask, float* obs) {
@@ -116,6 +121,7 @@ static int step_one(oracle* o, int i, const float* act, float* obs, float* rewar
     uint8_t dn = 0;
     if (o->sd[i].flags & PIH_FLAG_DONE) return 0;
     int nc = step_env_d(&o->md, &o->cd, &o->sd[i], a, off, gid, ob, &rw, &dn);
+    o->last_nc[i] = nc;
     if (obs) for (int k = 0; k < 5; ++k) obs[k] = (float)ob[k];
     if (reward) *reward = (float)rw;
     if (done) *done = dn;
@@ -125,6 +131,7 @@ static int step_one(oracle* o, int i, const float* act, float* obs, float* rewar
     uint8_t dn = 0;
     if (o->sf[i].flags & PIH_FLAG_DONE) return 0;
     int nc = step_env_f(&o->mf, &o->cf, &o->sf[i], act, &o->off[3 * i], gid, ob, &rw, &dn);
+    o->last_nc[i] = nc;
     if (obs) for (int k = 0; k < 5; ++k) obs[k] = ob[k];
     if (reward) *reward = rw;
     if (done) *done = dn;
@@ -182,6 +189,11 @@ int pih_oracle_rollout(void* h, int steps, float* obs, float* reward, uint8_t* d
   int rc = pih_oracle_rollout_range(h, steps, 0, o->cfg.num_envs, obs, reward, done, counters);
   if (rc == 0) o->global_step += (uint32_t)steps;
   return rc;
+}
+
+void pih_oracle_last_contacts(void* h, int* out) {
+  oracle* o = (oracle*)h;
+  for (int i = 0; i < o->cfg.num_envs; ++i) out[i] = o->last_nc[i];
 }
 
 /* state exchange in the device layout: words[slot][env][4] (float4 SoA, pih_constants.h) */

@@ -324,7 +324,7 @@ typedef struct {
 
 typedef struct {
   int task, arm, fly_object;
-  real dt;
+  real dt, solver_residual;
   int solver_iters, ik_iters, max_steps, auto_reset, action_frame_env;
   uint64_t seed;
 } FN(simcfg);
@@ -406,30 +406,35 @@ static void FN(ik_dls)(const model* M, const simcfg* C, const fkres* F0, const r
       v3 jv = FN(v3_cross)(z, d);
       J[0][j] = jv.x; J[1][j] = jv.y; J[2][j] = jv.z; J[3][j] = z.x; J[4][j] = z.y; J[5][j] = z.z;
     }
-    /* A = J J^T + lambda^2 I (upper triangle computed, mirrored), Cholesky, solve A y = e */
-    real A[6][6], L[6][6], invd[6], y[6];
+    /* A = J J^T + lambda^2 I (upper triangle computed, mirrored); A = L D L^T (unit L; W = L D), then
+     * L z = e, y = z / d, L^T x = y.  (Square-root-free form of the 6x6 SPD solve.) */
+    real A[6][6], L[6][6], W[6][6], invd[6], y[6];
     for (int a = 0; a < 6; ++a)
       for (int b = a; b < 6; ++b) {
         real s = (a == b) ? RC(PIH_IK_LAMBDA * PIH_IK_LAMBDA) : RC(0);
         for (int j = 0; j < n; ++j) s = FMA(J[a][j], J[b][j], s);
         A[a][b] = s; A[b][a] = s;
       }
-    for (int i = 0; i < 6; ++i)
-      for (int j = 0; j <= i; ++j) {
+    for (int i = 0; i < 6; ++i) {
+      for (int j = 0; j < i; ++j) {
         real s = A[i][j];
-        for (int kk = 0; kk < j; ++kk) s = FMA(-L[i][kk], L[j][kk], s);
-        if (i == j) { L[i][i] = SQRT(s); invd[i] = RC(1) / L[i][i]; }
-        else L[i][j] = s * invd[j];
+        for (int kk = 0; kk < j; ++kk) s = FMA(-W[i][kk], L[j][kk], s);
+        W[i][j] = s;
+        L[i][j] = s * invd[j];
       }
+      real d = A[i][i];
+      for (int kk = 0; kk < i; ++kk) d = FMA(-W[i][kk], L[i][kk], d);
+      invd[i] = RC(1) / d;
+    }
     for (int i = 0; i < 6; ++i) {
       real s = e[i];
       for (int kk = 0; kk < i; ++kk) s = FMA(-L[i][kk], y[kk], s);
-      y[i] = s * invd[i];
+      y[i] = s;
     }
     for (int i = 5; i >= 0; --i) {
-      real s = y[i];
+      real s = y[i] * invd[i];
       for (int kk = i + 1; kk < 6; ++kk) s = FMA(-L[kk][i], y[kk], s);
-      y[i] = s * invd[i];
+      y[i] = s;
     }
     real dth[NBM], mx = RC(0);
     for (int j = 0; j < n; ++j) {
@@ -868,7 +873,7 @@ typedef struct {
   v3 mang[3];       /* Iw^-1 (r x dir)                              */
   real ja[3][NBM];  /* arm Jacobian rows of v_arm(p) . dir          */
   real ma[3][NBM];  /* Minv ja^T                                    */
-  real dinv[3], b[3], lam[3], mu;
+  real dinv[3], diag[3], b[3], lam[3], mu;
 } FN(crow);
 #define crow FN(crow)
 
@@ -1002,11 +1007,17 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
     m_b[j] = (vstar - vs[j]) * m_dinv[j];
     m_lam[j] = RC(0);
     m_max[j] = M->maxf[j] * dt;
-    /* joint limits (btMultiBodyJointLimitConstraint [3P]): a row exists for each limit that is reachable this step:
-     * gap < |v*| dt + |v| dt + 0.02 ; inside the limit the joint may close the gap, outside it is pushed back with ERP */
-    real reachv = FMA(ABS(vstar) + ABS(S->qd[j]), dt, RC(0.02));
+    /* joint limits (btMultiBodyJointLimitConstraint [3P]): a row exists for each limit that can be reached this step,
+     * judged by the velocities that may drive the joint towards it (motor target v*, unconstrained velocity vs):
+     *   lower: gap < max(-v*, -vs, 0) dt + 0.005      upper: gap < max(v*, vs, 0) dt + 0.005
+     * inside the limit the joint may close the gap, outside it is pushed back with ERP */
     real glo = S->q[j] - M->lo[j], ghi = M->hi[j] - S->q[j];
-    l_on[0][j] = glo < reachv; l_on[1][j] = ghi < reachv;
+    real vdn = (-vstar > -vs[j]) ? -vstar : -vs[j];
+    vdn = (vdn > RC(0)) ? vdn : RC(0);
+    real vup = (vstar > vs[j]) ? vstar : vs[j];
+    vup = (vup > RC(0)) ? vup : RC(0);
+    l_on[0][j] = glo < FMA(vdn, dt, RC(0.005));
+    l_on[1][j] = ghi < FMA(vup, dt, RC(0.005));
     l_lam[0][j] = l_lam[1][j] = RC(0);
     real tlo = (glo > RC(0)) ? -(glo * idt) : -(RC(PIH_ERP) * glo * idt);
     real thi = (ghi > RC(0)) ? -(ghi * idt) : -(RC(PIH_ERP) * ghi * idt);
@@ -1059,6 +1070,7 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
         vrel = vrel + va;
       }
       r->dinv[d] = RC(1) / diag;
+      r->diag[d] = diag;
       real tv = RC(0);
       if (d == 0) tv = (c->dist > RC(0)) ? -(c->dist * idt) : -(RC(PIH_ERP) * c->dist * idt);
       r->b[d] = (tv - vrel) * r->dinv[d];
@@ -1069,13 +1081,18 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
   real dva[NBM];
   for (int j = 0; j < nb; ++j) dva[j] = RC(0);
   v3 dvl = FN(v3_make)(0, 0, 0), dvw = dvl;
+  /* early exit: PyBullet's solverResidualThreshold (default 1e-7) on the largest squared velocity change
+   * (deltaImpulse / jacDiagABInv)^2 of any row in the iteration [3P] */
   for (int it = 0; it < C->solver_iters; ++it) {
+    real res2 = RC(0);
+#define PIH_RES(dl_, diag_) do { real rv_ = (dl_) * (diag_); rv_ = rv_ * rv_; if (rv_ > res2) res2 = rv_; } while (0)
     for (int j = 0; j < nb; ++j) {
       real dl = FMA(-dva[j], m_dinv[j], m_b[j]);
       real s = m_lam[j] + dl;
       s = (s > m_max[j]) ? m_max[j] : ((s < -m_max[j]) ? -m_max[j] : s);
       dl = s - m_lam[j];
       m_lam[j] = s;
+      PIH_RES(dl, Minv[j][j]);
       for (int i = 0; i < nb; ++i) dva[i] = FMA(Minv[i][j], dl, dva[i]);
     }
     for (int j = 0; j < nb; ++j)
@@ -1087,6 +1104,7 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
         s = (s < RC(0)) ? RC(0) : s;
         dl = (s - l_lam[side][j]) * sg;
         l_lam[side][j] = s;
+        PIH_RES(dl, Minv[j][j]);
         for (int i = 0; i < nb; ++i) dva[i] = FMA(Minv[i][j], dl, dva[i]);
       }
     for (int pass = 0; pass < 2; ++pass)
@@ -1109,11 +1127,16 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
           }
           dl = s - r->lam[d];
           r->lam[d] = s;
+          PIH_RES(dl, r->diag[d]);
           if (r->has_fb) { dvl = FN(v3_axpy)(dl * im, r->dir[d], dvl); dvw = FN(v3_axpy)(dl, r->mang[d], dvw); }
           if (r->arm_body >= 0) for (int j = 0; j < nb; ++j) dva[j] = FMA(r->ma[d][j], dl, dva[j]);
         }
       }
+#undef PIH_RES
+    pih_dbg_pgs_iters += 1;
+    if (res2 <= C->solver_residual) break;
   }
+  pih_dbg_pgs_steps += 1;
   /* ---- integrate (semi-implicit Euler) ---- */
   for (int j = 0; j < nb; ++j) {
     real v = vs[j] + dva[j];

@@ -20,7 +20,7 @@ STATE_F4 = 10
 class PihConfig(C.Structure):
     """Mirror of ``pih_config`` (include/pih.h)."""
     _fields_ = [("task", C.c_int32), ("arm", C.c_int32), ("fly_object", C.c_int32), ("num_envs", C.c_int32),
-                ("sub_num", C.c_int32), ("env_id_base", C.c_int32), ("offset", C.c_float * 3), ("dt", C.c_float),
+                ("sub_num", C.c_int32), ("env_id_base", C.c_int32), ("offset", C.c_float * 3), ("dt", C.c_float), ("solver_residual", C.c_float),
                 ("solver_iters", C.c_int32), ("ik_iters", C.c_int32), ("max_steps", C.c_int32),
                 ("auto_reset", C.c_int32), ("action_frame_env", C.c_int32), ("device", C.c_int32),
                 ("seed", C.c_uint64)]
@@ -76,7 +76,7 @@ EXPORTS = ["pih_abi_version", "pih_state_words", "pih_action_dim", "pih_obs_dim"
 
 
 def make_config(num_envs, task="peg-in-hole", arm="panda", fly_object="banana", sub_num=None, env_id_base=0,
-                offset=(0.0, 0.0, 0.0), dt=1.0 / 240.0, solver_iters=50, ik_iters=20, max_steps=0, auto_reset=False,
+                offset=(0.0, 0.0, 0.0), dt=1.0 / 240.0, solver_residual=1e-7, solver_iters=50, ik_iters=20, max_steps=0, auto_reset=False,
                 action_frame_env=False, device=0, seed=0):
     c = PihConfig()
     c.task = TASK_IDS[task] if isinstance(task, str) else int(task)
@@ -87,6 +87,7 @@ def make_config(num_envs, task="peg-in-hole", arm="panda", fly_object="banana", 
     c.env_id_base = int(env_id_base)
     c.offset[:] = [float(v) for v in offset]
     c.dt = float(dt)
+    c.solver_residual = float(solver_residual)
     c.solver_iters, c.ik_iters, c.max_steps = int(solver_iters), int(ik_iters), int(max_steps)
     c.auto_reset, c.action_frame_env, c.device, c.seed = int(bool(auto_reset)), int(bool(action_frame_env)), int(device), int(seed)
     return c

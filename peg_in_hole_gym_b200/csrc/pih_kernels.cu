@@ -264,7 +264,7 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   if (cfg->num_envs <= 0 || cfg->sub_num <= 0) return PIH_ERR_INVALID;
   if (cfg->task != PIH_TASK_PEG_IN_HOLE && cfg->task != PIH_TASK_RANDOM_FLY) return PIH_ERR_INVALID;
   if (cfg->arm != PIH_ARM_PANDA && cfg->arm != PIH_ARM_UR5) return PIH_ERR_INVALID;
-  if (!(cfg->dt > 0.0f) || cfg->solver_iters < 0 || cfg->ik_iters < 0) return PIH_ERR_INVALID;
+  if (!(cfg->dt > 0.0f) || cfg->solver_iters < 0 || cfg->ik_iters < 0 || !(cfg->solver_residual >= 0.0f)) return PIH_ERR_INVALID;
   // reference assert: task_num == 1 or offset != [0,0,0] (envs/base_env.py:17)
   if (cfg->sub_num > 1 && cfg->offset[0] == 0.0f && cfg->offset[1] == 0.0f && cfg->offset[2] == 0.0f) return PIH_ERR_INVALID;
   int ndev = 0;
@@ -288,7 +288,7 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   P.grid_side = s > 0 ? s : 1;
   P.env_id_base = cfg->env_id_base;
   for (int k = 0; k < 3; ++k) P.offset[k] = cfg->offset[k];
-  P.dt = cfg->dt; P.idt = 1.0f / cfg->dt;
+  P.dt = cfg->dt; P.idt = 1.0f / cfg->dt; P.solver_residual = cfg->solver_residual;
   P.solver_iters = cfg->solver_iters; P.ik_iters = cfg->ik_iters; P.max_steps = cfg->max_steps;
   P.auto_reset = cfg->auto_reset; P.action_frame_env = cfg->action_frame_env;
   P.seed_lo = (unsigned)cfg->seed; P.seed_hi = (unsigned)(cfg->seed >> 32);

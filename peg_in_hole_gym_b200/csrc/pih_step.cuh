@@ -30,14 +30,17 @@ struct ContactSet {
   int n;
 };
 
-// keep the PIH_MAXC deepest candidates; ties keep the earlier candidate
-PIH_D void contact_push(ContactSet& S, const Contact& c) {
-  if (!(c.dist < (float)PIH_CONTACT_MARGIN)) return;
+// keep the PIH_MAXC deepest candidates; ties keep the earlier candidate.  The margin test is inlined at every
+// candidate site; the (rare) insertion is one out-of-line copy so that it does not bloat the instruction stream.
+__device__ __noinline__ void contact_insert(ContactSet& S, const Contact& c) {
   if (S.n < PIH_MAXC) { S.c[S.n++] = c; return; }
   int w = 0;
   for (int i = 1; i < PIH_MAXC; ++i)
     if (S.c[i].dist > S.c[w].dist) w = i;
   if (c.dist < S.c[w].dist) S.c[w] = c;
+}
+PIH_D void contact_push(ContactSet& S, const Contact& c) {
+  if (c.dist < (float)PIH_CONTACT_MARGIN) contact_insert(S, c);
 }
 
 PIH_D float sd_rect(float da, float db, float sa, float sb, float& na, float& nb_) {
@@ -258,7 +261,7 @@ template <int ARM> struct CRow {
   int has_fb, arm_body;
   v3 dir[3], jang[3], mang[3];
   float ja[3][ArmDims<ARM>::NB], ma[3][ArmDims<ARM>::NB];
-  float dinv[3], b[3], lam[3], mu;
+  float dinv[3], diag[3], b[3], lam[3], mu;
 };
 
 template <int ARM> PIH_D unsigned anc_rt(int body) {
@@ -389,7 +392,7 @@ template <int ARM> __device__ __noinline__ bool step_env(const SimParams& P, Env
   const float im = P.fb_im;
   // ---- motor + limit rows
   float m_dinv[nb], m_b[nb], m_lam[nb], m_max[nb], l_b[2][nb], l_lam[2][nb];
-  bool l_on[2][nb];  // [0] lower, [1] upper limit row present
+  unsigned l_on = 0u;  // bit 2j: lower limit row of joint j present, bit 2j+1: upper
 #pragma unroll
   for (int j = 0; j < nb; ++j) {
     // targets outside the URDF limits are unreachable: aim at the limit instead of fighting the limit row
@@ -400,9 +403,11 @@ template <int ARM> __device__ __noinline__ bool step_env(const SimParams& P, Env
     m_b[j] = (vstar - vs[j]) * m_dinv[j];
     m_lam[j] = 0.0f;
     m_max[j] = T.maxf[j] * dt;
-    float reachv = fmaf(fabsf(vstar) + fabsf(S.qd[j]), dt, 0.02f);
+    // a limit row exists only if the joint can reach that limit this step (see oracle for the rule)
     float glo = S.q[j] - T.lo[j], ghi = T.hi[j] - S.q[j];
-    l_on[0][j] = glo < reachv; l_on[1][j] = ghi < reachv;
+    float vdn = fmaxf(fmaxf(-vstar, -vs[j]), 0.0f), vup = fmaxf(fmaxf(vstar, vs[j]), 0.0f);
+    l_on |= (glo < fmaf(vdn, dt, 0.005f) ? 1u : 0u) << (2 * j);
+    l_on |= (ghi < fmaf(vup, dt, 0.005f) ? 1u : 0u) << (2 * j + 1);
     l_lam[0][j] = l_lam[1][j] = 0.0f;
     float tlo = (glo > 0.0f) ? -(glo * idt) : -((float)PIH_ERP * glo * idt);
     float thi = (ghi > 0.0f) ? -(ghi * idt) : -((float)PIH_ERP * ghi * idt);
@@ -414,11 +419,13 @@ template <int ARM> __device__ __noinline__ bool step_env(const SimParams& P, Env
   collide<ARM>(P, S, F, Rfb, CS);
   CRow<ARM> rows[PIH_MAXC];
   int pairmask = 0;
+  bool arm_contacts = false;
   v3 pfb = mk(S.ppos[0], S.ppos[1], S.ppos[2]);
   for (int k = 0; k < CS.n; ++k) {
     const Contact& c = CS.c[k];
     CRow<ARM>& r = rows[k];
     pairmask |= c.pair;
+    arm_contacts = arm_contacts || (c.arm_body >= 0);
     r.has_fb = c.has_fb; r.arm_body = c.arm_body; r.mu = c.mu;
     r.dir[0] = c.n;
     plane_space(c.n, r.dir[1], r.dir[2]);
@@ -463,72 +470,116 @@ template <int ARM> __device__ __noinline__ bool step_env(const SimParams& P, Env
         vrel = vrel + va;
       }
       r.dinv[d] = 1.0f / diag;
+      r.diag[d] = diag;
       float tv = 0.0f;
       if (d == 0) tv = (c.dist > 0.0f) ? -(c.dist * idt) : -((float)PIH_ERP * c.dist * idt);
       r.b[d] = (tv - vrel) * r.dinv[d];
       r.lam[d] = 0.0f;
     }
   }
-  // ---- projected Gauss-Seidel: motors, limits, contact normals, contact friction
+  // ---- projected Gauss-Seidel: motors, limits, contact normals, contact friction.  Early exit on PyBullet's
+  //      solverResidualThreshold: largest squared velocity change (deltaImpulse / jacDiagABInv)^2 of the iteration.
   float dva[nb];
 #pragma unroll
   for (int j = 0; j < nb; ++j) dva[j] = 0.0f;
   v3 dvl = mk(0.0f, 0.0f, 0.0f), dvw = dvl;
   const int ncon = CS.n;
   for (int it = 0; it < P.solver_iters; ++it) {
+    float res2 = 0.0f;
 #pragma unroll
     for (int j = 0; j < nb; ++j) {
       float dl = fmaf(-dva[j], m_dinv[j], m_b[j]);
       float s = m_lam[j] + dl;
-      s = (s > m_max[j]) ? m_max[j] : ((s < -m_max[j]) ? -m_max[j] : s);
+      s = fminf(fmaxf(s, -m_max[j]), m_max[j]);
       dl = s - m_lam[j];
       m_lam[j] = s;
+      float rv = dl * Minv[j][j];
+      res2 = fmaxf(res2, rv * rv);
 #pragma unroll
       for (int i = 0; i < nb; ++i) dva[i] = fmaf(Minv[i][j], dl, dva[i]);
     }
+    if (l_on) {  // uniform-ish skip: most steps only the finger limit rows exist
 #pragma unroll
-    for (int j = 0; j < nb; ++j) {
+      for (int j = 0; j < nb; ++j) {
 #pragma unroll
-      for (int side = 0; side < 2; ++side) {
-        if (!l_on[side][j]) continue;
-        float sg = side ? -1.0f : 1.0f;
-        float dl = fmaf(-(sg * dva[j]), m_dinv[j], l_b[side][j]);
-        float s = l_lam[side][j] + dl;
-        s = (s < 0.0f) ? 0.0f : s;
-        dl = (s - l_lam[side][j]) * sg;
-        l_lam[side][j] = s;
+        for (int side = 0; side < 2; ++side) {
+          if (!((l_on >> (2 * j + side)) & 1u)) continue;
+          float sg = side ? -1.0f : 1.0f;
+          float dl = fmaf(-(sg * dva[j]), m_dinv[j], l_b[side][j]);
+          float s = l_lam[side][j] + dl;
+          s = fmaxf(s, 0.0f);
+          dl = (s - l_lam[side][j]) * sg;
+          l_lam[side][j] = s;
+          float rv = dl * Minv[j][j];
+          res2 = fmaxf(res2, rv * rv);
 #pragma unroll
-        for (int i = 0; i < nb; ++i) dva[i] = fmaf(Minv[i][j], dl, dva[i]);
-      }
-    }
-    for (int pass = 0; pass < 2; ++pass)
-      for (int k = 0; k < ncon; ++k) {
-        CRow<ARM>& r = rows[k];
-        for (int d = (pass ? 1 : 0); d < (pass ? 3 : 1); ++d) {
-          float rel = 0.0f;
-          if (r.has_fb) rel = vdot(r.dir[d], dvl) + vdot(r.jang[d], dvw);
-          if (r.arm_body >= 0) {
-            float ra = 0.0f;
-#pragma unroll
-            for (int j = 0; j < nb; ++j) ra = fmaf(r.ja[d][j], dva[j], ra);
-            rel = rel + ra;
-          }
-          float dl = fmaf(-rel, r.dinv[d], r.b[d]);
-          float s = r.lam[d] + dl;
-          if (d == 0) s = (s < 0.0f) ? 0.0f : s;
-          else {
-            float lim = r.mu * r.lam[0];
-            s = (s > lim) ? lim : ((s < -lim) ? -lim : s);
-          }
-          dl = s - r.lam[d];
-          r.lam[d] = s;
-          if (r.has_fb) { dvl = vaxpy(dl * im, r.dir[d], dvl); dvw = vaxpy(dl, r.mang[d], dvw); }
-          if (r.arm_body >= 0) {
-#pragma unroll
-            for (int j = 0; j < nb; ++j) dva[j] = fmaf(r.ma[d][j], dl, dva[j]);
-          }
+          for (int i = 0; i < nb; ++i) dva[i] = fmaf(Minv[i][j], dl, dva[i]);
         }
       }
+    }
+    if (!arm_contacts) {
+      // common case: every contact is free body vs static geometry -> no per-row type branches, no arm coupling
+      for (int k = 0; k < ncon; ++k) {
+        CRow<ARM>& r = rows[k];
+        float rel = vdot(r.dir[0], dvl) + vdot(r.jang[0], dvw);
+        float dl = fmaf(-rel, r.dinv[0], r.b[0]);
+        float s = fmaxf(r.lam[0] + dl, 0.0f);
+        dl = s - r.lam[0];
+        r.lam[0] = s;
+        float rv = dl * r.diag[0];
+        res2 = fmaxf(res2, rv * rv);
+        dvl = vaxpy(dl * im, r.dir[0], dvl);
+        dvw = vaxpy(dl, r.mang[0], dvw);
+      }
+      for (int k = 0; k < ncon; ++k) {
+        CRow<ARM>& r = rows[k];
+        const float lim = r.mu * r.lam[0];
+#pragma unroll
+        for (int d = 1; d < 3; ++d) {
+          float rel = vdot(r.dir[d], dvl) + vdot(r.jang[d], dvw);
+          float dl = fmaf(-rel, r.dinv[d], r.b[d]);
+          float s = fminf(fmaxf(r.lam[d] + dl, -lim), lim);
+          dl = s - r.lam[d];
+          r.lam[d] = s;
+          float rv = dl * r.diag[d];
+          res2 = fmaxf(res2, rv * rv);
+          dvl = vaxpy(dl * im, r.dir[d], dvl);
+          dvw = vaxpy(dl, r.mang[d], dvw);
+        }
+      }
+    } else {
+      for (int pass = 0; pass < 2; ++pass)
+        for (int k = 0; k < ncon; ++k) {
+          CRow<ARM>& r = rows[k];
+          for (int d = (pass ? 1 : 0); d < (pass ? 3 : 1); ++d) {
+            float rel = 0.0f;
+            if (r.has_fb) rel = vdot(r.dir[d], dvl) + vdot(r.jang[d], dvw);
+            if (r.arm_body >= 0) {
+              float ra = 0.0f;
+#pragma unroll
+              for (int j = 0; j < nb; ++j) ra = fmaf(r.ja[d][j], dva[j], ra);
+              rel = rel + ra;
+            }
+            float dl = fmaf(-rel, r.dinv[d], r.b[d]);
+            float s = r.lam[d] + dl;
+            if (d == 0) s = fmaxf(s, 0.0f);
+            else {
+              float lim = r.mu * r.lam[0];
+              s = fminf(fmaxf(s, -lim), lim);
+            }
+            dl = s - r.lam[d];
+            r.lam[d] = s;
+            float rv = dl * r.diag[d];
+            res2 = fmaxf(res2, rv * rv);
+            if (r.has_fb) { dvl = vaxpy(dl * im, r.dir[d], dvl); dvw = vaxpy(dl, r.mang[d], dvw); }
+            if (r.arm_body >= 0) {
+#pragma unroll
+              for (int j = 0; j < nb; ++j) dva[j] = fmaf(r.ma[d][j], dl, dva[j]);
+            }
+          }
+        }
+    }
+    if (res2 <= P.solver_residual) break;
   }
   // ---- integrate
 #pragma unroll

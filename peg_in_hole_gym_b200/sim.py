@@ -16,14 +16,14 @@ class BatchedSim:
     ``state[10, N, 4]`` (layout: csrc/pih_constants.h); outputs in ``obs[N,5]``, ``reward[N]``, ``done[N]``."""
 
     def __init__(self, num_envs, task="peg-in-hole", arm="panda", fly_object="banana", sub_num=None, env_id_base=0,
-                 offset=(0.0, 0.0, 0.0), dt=1.0 / 240.0, solver_iters=50, ik_iters=20, max_steps=0, auto_reset=False,
+                 offset=(0.0, 0.0, 0.0), dt=1.0 / 240.0, solver_residual=1e-7, solver_iters=50, ik_iters=20, max_steps=0, auto_reset=False,
                  action_frame_env=False, device=None, seed=0):
         L = N.lib()
         if not torch.cuda.is_available():
             raise N.PihError("peg_in_hole_gym_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
-        self.cfg = N.make_config(num_envs, task, arm, fly_object, sub_num, env_id_base, offset, dt, solver_iters,
-                                 ik_iters, max_steps, auto_reset, action_frame_env, self.device.index, seed)
+        self.cfg = N.make_config(num_envs, task, arm, fly_object, sub_num, env_id_base, offset, dt, solver_residual,
+                                 solver_iters, ik_iters, max_steps, auto_reset, action_frame_env, self.device.index, seed)
         self.n = int(num_envs)
         self.action_dim = L.pih_action_dim(self.cfg.arm)
         self.obs_dim = L.pih_obs_dim()

@@ -15,7 +15,7 @@ def load(prefix):
     out = {}
     for m in re.finditer(r"#define PIH_%s_(\w+) (-?\d+)" % prefix, txt):
         out[m.group(1)] = int(m.group(2))
-    for m in re.finditer(r"static const (int|double) PIH_%s_(\w+)((?:\[\d+\])+) = (.*?);" % prefix, txt, re.S):
+    for m in re.finditer(r"(?:static const|PIH_TABLE) (int|double) PIH_%s_(\w+)((?:\[\d+\])+) = (.*?);" % prefix, txt, re.S):
         dims = [int(d) for d in re.findall(r"\[(\d+)\]", m.group(3))]
         vals = [float(v) for v in re.findall(r"-?\d+\.?\d*(?:e-?\d+)?", m.group(4))]
         a = np.array(vals).reshape(dims)

@@ -13,14 +13,14 @@ LIB = os.path.join(ORACLE_DIR, "libpih_oracle.so")
 class PihConfig(C.Structure):
     """Mirror of include/pih.h: pih_config."""
     _fields_ = [("task", C.c_int32), ("arm", C.c_int32), ("fly_object", C.c_int32), ("num_envs", C.c_int32),
-                ("sub_num", C.c_int32), ("env_id_base", C.c_int32), ("offset", C.c_float * 3), ("dt", C.c_float),
+                ("sub_num", C.c_int32), ("env_id_base", C.c_int32), ("offset", C.c_float * 3), ("dt", C.c_float), ("solver_residual", C.c_float),
                 ("solver_iters", C.c_int32), ("ik_iters", C.c_int32), ("max_steps", C.c_int32),
                 ("auto_reset", C.c_int32), ("action_frame_env", C.c_int32), ("device", C.c_int32),
                 ("seed", C.c_uint64)]
 
 
 def make_config(num_envs, task=0, arm=0, fly_object=0, sub_num=None, env_id_base=0, offset=(0.0, 0.0, 0.0),
-                dt=1.0 / 240.0, solver_iters=50, ik_iters=20, max_steps=0, auto_reset=0, action_frame_env=0,
+                dt=1.0 / 240.0, solver_residual=1e-7, solver_iters=50, ik_iters=20, max_steps=0, auto_reset=0, action_frame_env=0,
                 device=0, seed=0):
     c = PihConfig()
     c.task, c.arm, c.fly_object, c.num_envs = task, arm, fly_object, num_envs
@@ -28,6 +28,7 @@ def make_config(num_envs, task=0, arm=0, fly_object=0, sub_num=None, env_id_base
     c.env_id_base = env_id_base
     c.offset[:] = [float(v) for v in offset]
     c.dt = dt
+    c.solver_residual = solver_residual
     c.solver_iters, c.ik_iters, c.max_steps, c.auto_reset = solver_iters, ik_iters, max_steps, auto_reset
     c.action_frame_env, c.device, c.seed = action_frame_env, device, seed
     return c

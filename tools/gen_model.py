@@ -237,32 +237,32 @@ def emit_arm(f, P, m, n_arm, rest, kp, maxforce, max_sph, max_box):
     f.write(f"#define PIH_{P}_NSPH {len(m['spheres'])}\n#define PIH_{P}_NBOX {len(m['boxes'])}\n")
     f.write(f"#define PIH_{P}_PARENT_LIST " + ", ".join(str(b["parent"]) for b in B) + "\n")
     f.write(f"#define PIH_{P}_JTYPE_LIST " + ", ".join(str(b["jtype"]) for b in B) + "\n")
-    f.write(f"static const int PIH_{P}_PARENT[{nb}] = {{" + ", ".join(str(b["parent"]) for b in B) + "};\n")
-    f.write(f"static const int PIH_{P}_JTYPE[{nb}] = {{" + ", ".join(str(b["jtype"]) for b in B) + "};\n")
-    f.write(f"static const double PIH_{P}_R0[{nb}][9] = {{" + ",\n  ".join(fmt(b["R0"]) for b in B) + "};\n")
-    f.write(f"static const double PIH_{P}_T0[{nb}][3] = {{" + ", ".join(fmt(b["t0"]) for b in B) + "};\n")
-    f.write(f"static const double PIH_{P}_MASS[{nb}] = " + fmt([b["mass"] for b in B]) + ";\n")
-    f.write(f"static const double PIH_{P}_H[{nb}][3] = {{" + ", ".join(fmt(b["h"]) for b in B) + "};\n")
-    f.write(f"static const double PIH_{P}_IROT[{nb}][9] = {{" + ",\n  ".join(fmt(b["Irot"]) for b in B) + "};\n")
-    f.write(f"static const double PIH_{P}_LO[{nb}] = " + fmt([b["lo"] for b in B]) + ";\n")
-    f.write(f"static const double PIH_{P}_HI[{nb}] = " + fmt([b["hi"] for b in B]) + ";\n")
-    f.write(f"static const double PIH_{P}_DAMP[{nb}] = " + fmt([b["damping"] for b in B]) + ";\n")
-    f.write(f"static const double PIH_{P}_MAXF[{nb}] = " + fmt(maxforce) + ";\n")
-    f.write(f"static const double PIH_{P}_KP[{nb}] = " + fmt(kp) + ";\n")
-    f.write(f"static const double PIH_{P}_REST[{nb}] = " + fmt(rest) + ";\n")
-    f.write(f"static const double PIH_{P}_EE_R[9] = " + fmt(m["ee_R"]) + ";\n")
-    f.write(f"static const double PIH_{P}_EE_T[3] = " + fmt(m["ee_t"]) + ";\n")
+    f.write(f"PIH_TABLE int PIH_{P}_PARENT[{nb}] = {{" + ", ".join(str(b["parent"]) for b in B) + "};\n")
+    f.write(f"PIH_TABLE int PIH_{P}_JTYPE[{nb}] = {{" + ", ".join(str(b["jtype"]) for b in B) + "};\n")
+    f.write(f"PIH_TABLE double PIH_{P}_R0[{nb}][9] = {{" + ",\n  ".join(fmt(b["R0"]) for b in B) + "};\n")
+    f.write(f"PIH_TABLE double PIH_{P}_T0[{nb}][3] = {{" + ", ".join(fmt(b["t0"]) for b in B) + "};\n")
+    f.write(f"PIH_TABLE double PIH_{P}_MASS[{nb}] = " + fmt([b["mass"] for b in B]) + ";\n")
+    f.write(f"PIH_TABLE double PIH_{P}_H[{nb}][3] = {{" + ", ".join(fmt(b["h"]) for b in B) + "};\n")
+    f.write(f"PIH_TABLE double PIH_{P}_IROT[{nb}][9] = {{" + ",\n  ".join(fmt(b["Irot"]) for b in B) + "};\n")
+    f.write(f"PIH_TABLE double PIH_{P}_LO[{nb}] = " + fmt([b["lo"] for b in B]) + ";\n")
+    f.write(f"PIH_TABLE double PIH_{P}_HI[{nb}] = " + fmt([b["hi"] for b in B]) + ";\n")
+    f.write(f"PIH_TABLE double PIH_{P}_DAMP[{nb}] = " + fmt([b["damping"] for b in B]) + ";\n")
+    f.write(f"PIH_TABLE double PIH_{P}_MAXF[{nb}] = " + fmt(maxforce) + ";\n")
+    f.write(f"PIH_TABLE double PIH_{P}_KP[{nb}] = " + fmt(kp) + ";\n")
+    f.write(f"PIH_TABLE double PIH_{P}_REST[{nb}] = " + fmt(rest) + ";\n")
+    f.write(f"PIH_TABLE double PIH_{P}_EE_R[9] = " + fmt(m["ee_R"]) + ";\n")
+    f.write(f"PIH_TABLE double PIH_{P}_EE_T[3] = " + fmt(m["ee_t"]) + ";\n")
     sp = m["spheres"] + [(0, np.zeros(3), 0.0)] * (max_sph - len(m["spheres"]))
     f.write(f"#define PIH_{P}_SPH_BODY_LIST " + ", ".join(str(s[0]) for s in sp) + "\n")
-    f.write(f"static const int PIH_{P}_SPH_BODY[{max_sph}] = {{" + ", ".join(str(s[0]) for s in sp) + "};\n")
-    f.write(f"static const double PIH_{P}_SPH_C[{max_sph}][3] = {{" + ", ".join(fmt(s[1]) for s in sp) + "};\n")
-    f.write(f"static const double PIH_{P}_SPH_R[{max_sph}] = " + fmt([s[2] for s in sp]) + ";\n")
+    f.write(f"PIH_TABLE int PIH_{P}_SPH_BODY[{max_sph}] = {{" + ", ".join(str(s[0]) for s in sp) + "};\n")
+    f.write(f"PIH_TABLE double PIH_{P}_SPH_C[{max_sph}][3] = {{" + ", ".join(fmt(s[1]) for s in sp) + "};\n")
+    f.write(f"PIH_TABLE double PIH_{P}_SPH_R[{max_sph}] = " + fmt([s[2] for s in sp]) + ";\n")
     bx = m["boxes"] + [(0, np.zeros(3), np.eye(3), np.zeros(3))] * (max_box - len(m["boxes"]))
     f.write(f"#define PIH_{P}_BOX_BODY_LIST " + ", ".join(str(s[0]) for s in bx) + "\n")
-    f.write(f"static const int PIH_{P}_BOX_BODY[{max_box}] = {{" + ", ".join(str(s[0]) for s in bx) + "};\n")
-    f.write(f"static const double PIH_{P}_BOX_C[{max_box}][3] = {{" + ", ".join(fmt(s[1]) for s in bx) + "};\n")
-    f.write(f"static const double PIH_{P}_BOX_R[{max_box}][9] = {{" + ",\n  ".join(fmt(s[2]) for s in bx) + "};\n")
-    f.write(f"static const double PIH_{P}_BOX_H[{max_box}][3] = {{" + ", ".join(fmt(s[3]) for s in bx) + "};\n\n")
+    f.write(f"PIH_TABLE int PIH_{P}_BOX_BODY[{max_box}] = {{" + ", ".join(str(s[0]) for s in bx) + "};\n")
+    f.write(f"PIH_TABLE double PIH_{P}_BOX_C[{max_box}][3] = {{" + ", ".join(fmt(s[1]) for s in bx) + "};\n")
+    f.write(f"PIH_TABLE double PIH_{P}_BOX_R[{max_box}][9] = {{" + ",\n  ".join(fmt(s[2]) for s in bx) + "};\n")
+    f.write(f"PIH_TABLE double PIH_{P}_BOX_H[{max_box}][3] = {{" + ", ".join(fmt(s[3]) for s in bx) + "};\n\n")
 
 
 def main():
@@ -296,7 +296,9 @@ def main():
                 " * and the CUDA kernels.  Sources: reference ur5.urdf (in tree) and a restated Franka Panda table\n"
                 " * ([3P] pybullet_data, from memory, UNVERIFIED).  Frames: body origin at joint origin, z = joint axis. */\n"
                 "#ifndef PIH_MODEL_DATA_H\n#define PIH_MODEL_DATA_H\n\n")
-        f.write(f"#define PIH_MAX_SPH {MAX_SPH}\n#define PIH_MAX_BOX {MAX_BOX}\n\n")
+        f.write(f"#define PIH_MAX_SPH {MAX_SPH}\n#define PIH_MAX_BOX {MAX_BOX}\n"
+                "/* C++: constexpr so that kernels can dispatch on structural zeros at compile time */\n"
+                "#ifdef __cplusplus\n#define PIH_TABLE static constexpr\n#else\n#define PIH_TABLE static const\n#endif\n\n")
         emit_arm(f, "PANDA", pm, 7, p_rest, p_kp, p_maxf, MAX_SPH, MAX_BOX)
         emit_arm(f, "UR5", um, 6, u_rest, u_kp, u_maxf, MAX_SPH, MAX_BOX)
         f.write("#endif\n")
