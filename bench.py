@@ -39,6 +39,7 @@ SEED = 0
 # algorithmic cost per env-step (SURVEY.md 8d formula)
 BYTES_PER_ENV_STEP = 2 * 160 + 16 + 20 + 4 + 1   # float4-SoA state read+write (10 slots), action, obs, reward, done
 FLOPS_BULLET_DEFAULT = 2.2e5                       # I_ik=20, I_pgs=50, n=9, R=33
+NCU_TRAFFIC_BYTES = 922368                         # k_step<panda>, 4096 envs: DRAM read 922 KB + write 0 B per launch (profiles/)
 
 
 def flops_per_env_step(n=9, na=7, i_ik=20, i_pgs=50, rows=17):
@@ -121,20 +122,20 @@ def run_reference(args):
     if rank != 0:
         return
     threads = host_threads()
-    # one bench "step" = one env.step of the sample batch; sample sized for a few seconds per step-block
-    n = max(threads * 8, 64)
+    # same config as the b200 arm: 4096 panda sub-envs; one bench "step" = one env.step of that batch, run in blocks
+    n = args.envs_per_gpu
     block = 25
     import oracle_lib as ol
     ol.lib()
-    for _ in range(max(args.warmup // block, 1)):
+    for _ in range(max(min(args.warmup, 50) // block, 1)):
         cpu_oracle_rate(n, block, threads)
-    t_steps = max(args.steps // block, 1) * block
+    t_steps = max(min(args.steps, 400) // block, 1) * block      # bounded: a few seconds to a minute of host time
     rate, dt = cpu_oracle_rate(n, t_steps, threads)
     line = {"impl": "reference", "metric": "peg-in-hole env-steps/sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / t_steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "peg-in-hole panda, dt 1/240, 200-step episodes, U[-1,1]^4 actions (config 2 shape)",
-                       "envs": n, "note": "PyBullet not installable (no wheel/network): CPU restatement (oracle/), not PyBullet"},
+                       "envs_per_gpu": n, "total_envs": n, "note": "PyBullet not installable (no wheel/network): CPU restatement (oracle/), not PyBullet"},
             "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
                              "sample": f"{n} envs x {t_steps} steps, {threads} host threads"},
             "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -272,15 +273,11 @@ def main():
         cpu = None
         if not args.no_cpu and world == 1:
             thr = host_threads()
-            cn = max(thr * 8, 64)
-            cpu_oracle_rate(cn, 10, thr)
-            cst = 100
+            cn, cst = n, MAX_STEPS                      # one full 200-step episode of the same 4096-env batch (~20 CPU-seconds)
+            cpu_oracle_rate(min(cn, 512), 10, thr)
             crate, cdt = cpu_oracle_rate(cn, cst, thr)
-            if cdt < 5.0:
-                cst = int(min(4000, cst * 10.0 / max(cdt, 1e-3)))
-                crate, cdt = cpu_oracle_rate(cn, cst, thr)
             cpu = {"value": crate, "unit": "env-steps/s", "cores": thr, "kind": "port",
-                   "sample": f"CPU restatement (oracle/, not PyBullet): {cn} envs x {cst} steps of the same workload on {thr} host threads, {cdt:.1f} s"}
+                   "sample": f"CPU restatement (oracle/, not PyBullet): {cn} envs x {cst} steps of the same workload on {thr} host threads, {cdt:.1f} s wall"}
         line = {
             "metric": "peg-in-hole env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -294,7 +291,8 @@ def main():
                     "d2h_bytes_per_step": n * (20 + 4 + 1), "steps": e2e_steps, "timing": "wall clock incl. pinned staging + H2D + step + D2H + sync"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": (ach_tf / peak_tf) if peak_tf else None, "traffic": None,
+                         "frac": (ach_tf / peak_tf) if peak_tf else None, "traffic": NCU_TRAFFIC_BYTES if (args.arm == "panda" and n == ENVS_PER_GPU) else None,
+                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_kstep_ncu_full.csv",
                          "peak_source": "in-run FFMA probe (pih_measure_fp32_peak); FP32 pipe is not in MEASURED_PEAKS.json",
                          "flops_per_env_step": f_run, "flops_per_env_step_bullet_default": FLOPS_BULLET_DEFAULT,
                          "kernel": "pih::k_step<panda>", "kernel_us": kern_s * 1e6,

@@ -214,6 +214,13 @@ int pih_oracle_get_state(void* h, float* words) {
       words[WIDX(PIH_S_PANG + k, i, n)] = o->use_double ? (float)o->sd[i].pang[k] : o->sf[i].pang[k];
     }
     for (int k = 0; k < 4; ++k) words[WIDX(PIH_S_PQUAT + k, i, n)] = o->use_double ? (float)o->sd[i].pquat[k] : o->sf[i].pquat[k];
+    {
+      int32_t fs = o->use_double ? o->sd[i].fsm_state : o->sf[i].fsm_state, ft = o->use_double ? o->sd[i].fsm_t : o->sf[i].fsm_t;
+      memcpy(&words[WIDX(PIH_S_FSM_STATE, i, n)], &fs, 4);
+      memcpy(&words[WIDX(PIH_S_FSM_T, i, n)], &ft, 4);
+      words[WIDX(PIH_S_RANDY, i, n)] = o->use_double ? (float)o->sd[i].rand_y : o->sf[i].rand_y;
+      for (int k = 0; k < 7; ++k) words[WIDX(PIH_S_MTGT + k, i, n)] = o->use_double ? (float)o->sd[i].mtgt[k] : o->sf[i].mtgt[k];
+    }
     ints[0] = o->use_double ? o->sd[i].step : o->sf[i].step;
     ints[1] = o->use_double ? o->sd[i].episode : o->sf[i].episode;
     ints[2] = o->use_double ? o->sd[i].flags : o->sf[i].flags;
@@ -242,6 +249,14 @@ int pih_oracle_set_state(void* h, const float* words) {
       o->sf[i].pang[k] = words[WIDX(PIH_S_PANG + k, i, n)]; o->sd[i].pang[k] = o->sf[i].pang[k];
     }
     for (int k = 0; k < 4; ++k) { o->sf[i].pquat[k] = words[WIDX(PIH_S_PQUAT + k, i, n)]; o->sd[i].pquat[k] = o->sf[i].pquat[k]; }
+    {
+      int32_t fs, ft;
+      memcpy(&fs, &words[WIDX(PIH_S_FSM_STATE, i, n)], 4);
+      memcpy(&ft, &words[WIDX(PIH_S_FSM_T, i, n)], 4);
+      o->sf[i].fsm_state = o->sd[i].fsm_state = fs; o->sf[i].fsm_t = o->sd[i].fsm_t = ft;
+      o->sf[i].rand_y = words[WIDX(PIH_S_RANDY, i, n)]; o->sd[i].rand_y = o->sf[i].rand_y;
+      for (int k = 0; k < 7; ++k) { o->sf[i].mtgt[k] = words[WIDX(PIH_S_MTGT + k, i, n)]; o->sd[i].mtgt[k] = o->sf[i].mtgt[k]; }
+    }
     o->sf[i].step = o->sd[i].step = ints[0];
     o->sf[i].episode = o->sd[i].episode = ints[1];
     o->sf[i].flags = o->sd[i].flags = ints[2];

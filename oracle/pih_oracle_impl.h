@@ -100,6 +100,17 @@ static inline real FN(det_atan2_q1)(real y, real x) {
 #endif
 }
 
+/* full-range atan2 from the first-quadrant kernel */
+static inline real FN(det_atan2)(real y, real x) {
+#if REAL_IS_DOUBLE
+  return atan2(y, x);
+#else
+  float a = FN(det_atan2_q1)(y < 0.0f ? -y : y, x < 0.0f ? -x : x);
+  if (x < 0.0f) a = 3.1415927410125732421875f - a;
+  return (y < 0.0f) ? -a : a;
+#endif
+}
+
 /* ------------------------------------------------------------------ Philox4x32-10 (Random123) */
 #ifndef PIH_ORACLE_PHILOX
 #define PIH_ORACLE_PHILOX
@@ -319,6 +330,8 @@ typedef struct {
   real q[NBM], qd[NBM];
   real ppos[3], pquat[4], pvel[3], pang[3];
   int32_t step, episode, flags;
+  int32_t fsm_state, fsm_t;   /* scripted task */
+  real rand_y, mtgt[7];
 } FN(envstate);
 #define envstate FN(envstate)
 
@@ -770,7 +783,7 @@ static void FN(collide)(const model* M, const simcfg* C, const envstate* S, cons
   }
   /* (2) peg vs annular hole (peg-in-hole task only): peg rim points against the hole solid, hole rim points
    *     against the peg solid; broadphase on centre distance */
-  if (C->task == PIH_TASK_PEG_IN_HOLE) {
+  if (C->task != PIH_TASK_RANDOM_FLY) {
     v3 hc = FN(v3_make)(RC(PIH_HOLE_X), RC(PIH_HOLE_Y), RC(PIH_HOLE_Z));
     v3 dh = FN(v3_sub)(pfb, hc);
     const real reach = RC(PIH_PEG_HL + PIH_PEG_R + PIH_HOLE_ROUT + PIH_HOLE_HL + PIH_CONTACT_MARGIN);
@@ -883,7 +896,7 @@ static void FN(reset_env)(const model* M, const simcfg* C, envstate* S, uint32_t
   float u[4];
   pih_rng4(C->seed, gid, (uint32_t)S->episode, PIH_STREAM_RESET, u);
   for (int i = 0; i < NBM; ++i) { S->q[i] = (i < M->nb) ? M->rest[i] : RC(0); S->qd[i] = RC(0); }
-  if (C->task == PIH_TASK_PEG_IN_HOLE) {
+  if (C->task != PIH_TASK_RANDOM_FLY) {
     S->ppos[0] = (real)fmaf(u[0], 0.4f, -0.2f);   /* random.uniform(-0.2, 0.2)  peg_in_hole.py:239 */
     S->ppos[1] = (real)fmaf(u[1], 0.2f, -0.6f);   /* random.uniform(-0.4,-0.6)  peg_in_hole.py:239 */
     S->ppos[2] = RC(PIH_PEG_SPAWN_Z);
@@ -910,6 +923,10 @@ static void FN(reset_env)(const model* M, const simcfg* C, envstate* S, uint32_t
   S->pang[0] = S->pang[1] = S->pang[2] = RC(0);
   S->step = 0;
   S->flags = 0;
+  /* scripted task: cur_state 0, random_vector = [0, U(-0.03, 0.03), 0] (peg_in_hole.py:255-267) */
+  S->fsm_state = 0; S->fsm_t = 0;
+  S->rand_y = (real)fmaf(u[3], 0.06f, -0.03f);
+  for (int i = 0; i < 7; ++i) S->mtgt[i] = (i < M->narm) ? M->rest[i] : RC(0);
 }
 
 static void FN(observe)(const model* M, const simcfg* C, const envstate* S, const real off[3], real* obs) {
@@ -938,8 +955,56 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
   FN(ee_pose)(M, &F, &pee, &Ree);
   v3 tgt;
   real tq[4];
-  real qstar[NBM];
-  {
+  real qstar[NBM], kpc[NBM], mfc[NBM];
+  int fsm_done = 0;
+  for (int j = 0; j < nb; ++j) { kpc[j] = M->kp[j]; mfc[j] = M->maxf[j]; }
+  if (C->task == PIH_TASK_SCRIPTED) {
+    /* The task the reference ships: apply_action is `pass` (peg_in_hole.py:30-31) and the arm is driven by the
+     * scripted grasp->insert state machine of random_grasp/grasp_process (peg_in_hole.py:39-212).  One engine step
+     * here = one pass of its `while not done` loop body: update_state, grasp target, grasp_process, stepSimulation. */
+    static const int fsm_steps[PIH_FSM_NSTATES] = {PIH_FSM_STEPS_LIST};
+    if (S->fsm_t == fsm_steps[S->fsm_state]) {                      /* update_state, peg_in_hole.py:206-212 */
+      S->fsm_state += 1; S->fsm_t = 0;
+      if (S->fsm_state >= PIH_FSM_NSTATES) S->fsm_state = 0;
+    }
+    S->fsm_t += 1;
+    const int st = S->fsm_state;
+    /* grasp point = COM of the grasp link + R(q) random_vector; yaw of that link (peg_in_hole.py:58-62,125,215-225) */
+    m3 Rp = FN(quat_to_m3)(S->pquat);
+    v3 tp = FN(m3_v_add)(&Rp, FN(v3_make)(RC(0), S->rand_y, RC(0)), FN(v3_make)(S->ppos[0], S->ppos[1], S->ppos[2]));
+    real qx = S->pquat[0], qy = S->pquat[1], qz = S->pquat[2], qw = S->pquat[3];
+    real yaw = FN(det_atan2)(RC(2) * FMA(qx, qy, qw * qz), FMA(qw, qw, qx * qx) - FMA(qy, qy, qz * qz));
+    real cur[3] = {pee.x, pee.y, pee.z}, tar[3] = {tp.x, tp.y, tp.z}, res[3];
+    int arm_cmd = 0, clamp = 1;
+    real yaw_cmd = RC(0), zoff = RC(0);
+    if (st == 1 || st == 2) { arm_cmd = 1; yaw_cmd = RC(1.5707963267948966) + yaw; zoff = (st == 1) ? RC(0.05) : RC(-0.01); }
+    else if (st == 4 || st == 5 || st == 6) {
+      arm_cmd = 1; yaw_cmd = RC(-3.141592653589793);
+      tar[0] = RC(PIH_HOLE_X) - ((st == 4) ? RC(0.2) : ((st == 5) ? RC(0.04) : RC(0)));
+      tar[1] = RC(PIH_HOLE_Y); tar[2] = RC(PIH_HOLE_Z);
+      clamp = (st != 6);
+    } else if (st == 8) { arm_cmd = 1; yaw_cmd = RC(1.5707963267948966); tar[0] = RC(0.2); tar[1] = RC(-0.6); tar[2] = RC(0.4); clamp = 0; }
+    else if (st == 9) fsm_done = 1;
+    if (arm_cmd) {
+      for (int i = 0; i < 3; ++i) {                                   /* vel_constraint(cur, target, self.dv) */
+        real diff = tar[i] - cur[i];
+        if (clamp && ABS(diff) > RC(PIH_FSM_DV)) res[i] = cur[i] + ((diff > RC(0)) ? RC(PIH_FSM_DV) : RC(-PIH_FSM_DV));
+        else res[i] = cur[i] + diff;
+      }
+      tgt = FN(v3_make)(res[0], res[1], res[2] + zoff);
+      FN(euler_to_quat)(RC(0), RC(-3.141592653589793), yaw_cmd, tq);
+      real qik[NBM];
+      FN(ik_dls)(M, C, &F, S->q, tgt, tq, qik);
+      for (int j = 0; j < M->narm && j < 7; ++j) S->mtgt[j] = qik[j];
+    }
+    for (int j = 0; j < M->narm; ++j) { qstar[j] = S->mtgt[j < 7 ? j : 0]; kpc[j] = RC(PIH_FSM_KP); mfc[j] = RC(PIH_FSM_ARM_FORCE); }
+    int closed = (st >= 3 && st <= 6);
+    for (int j = M->narm; j < nb; ++j) {
+      qstar[j] = closed ? RC(PIH_FSM_FINGER_CLOSED) : RC(PIH_FSM_FINGER_OPEN);
+      kpc[j] = RC(PIH_FSM_KP);
+      mfc[j] = closed ? RC(PIH_FSM_FINGER_FORCE_HI) : RC(PIH_FSM_FINGER_FORCE_LO);
+    }
+  } else {
     real ax = action[0], ay = action[1], az = action[2];
     if (!C->action_frame_env) { ax = ax - off[0]; ay = ay - off[1]; az = az - off[2]; }
     if (C->arm == PIH_ARM_PANDA) {
@@ -1002,11 +1067,11 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
      * limit instead of fighting the limit row with its 1e5 N force cap (NEW, keeps PGS well conditioned) */
     real qt = qstar[j];
     qt = (qt < M->lo[j]) ? M->lo[j] : ((qt > M->hi[j]) ? M->hi[j] : qt);
-    real vstar = M->kp[j] * (qt - S->q[j]) * idt;
+    real vstar = kpc[j] * (qt - S->q[j]) * idt;
     m_dinv[j] = RC(1) / Minv[j][j];
     m_b[j] = (vstar - vs[j]) * m_dinv[j];
     m_lam[j] = RC(0);
-    m_max[j] = M->maxf[j] * dt;
+    m_max[j] = mfc[j] * dt;
     /* joint limits (btMultiBodyJointLimitConstraint [3P]): a row exists for each limit that can be reached this step,
      * judged by the velocities that may drive the joint towards it (motor target v*, unconstrained velocity vs):
      *   lower: gap < max(-v*, -vs, 0) dt + 0.005      upper: gap < max(v*, vs, 0) dt + 0.005
@@ -1171,7 +1236,7 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
   v3 pee2; m3 Ree2;
   FN(fk)(M, S->q, nb, &F2);
   FN(ee_pose)(M, &F2, &pee2, &Ree2);
-  if (C->task == PIH_TASK_PEG_IN_HOLE) {
+  if (C->task != PIH_TASK_RANDOM_FLY) {
     v3 d = FN(v3_make)(S->ppos[0] - RC(PIH_HOLE_X), S->ppos[1] - RC(PIH_HOLE_Y), S->ppos[2] - RC(PIH_HOLE_Z));
     success = FN(v3_dot)(d, d) < RC(PIH_SUCCESS_RADIUS * PIH_SUCCESS_RADIUS);
     rew = success ? RC(1) : RC(0);
@@ -1183,6 +1248,9 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
   }
   int dn = success || (C->max_steps > 0 && S->step >= C->max_steps);
   if (C->task == PIH_TASK_RANDOM_FLY && (pairmask & PIH_PAIR_PEG_TABLE)) dn = 1;
+  /* scripted task: the episode ends when the FSM reaches state 9 (peg_in_hole.py:203-204); the reward is the success
+   * test evaluated then (peg_in_hole.py:114-117) */
+  if (C->task == PIH_TASK_SCRIPTED) dn = fsm_done || (C->max_steps > 0 && S->step >= C->max_steps);
   S->flags = (dn ? PIH_FLAG_DONE : 0) | (success ? PIH_FLAG_SUCCESS : 0) | (pairmask << PIH_PAIR_SHIFT);
   *reward = rew;
   *done = (uint8_t)dn;

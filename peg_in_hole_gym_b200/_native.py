@@ -11,10 +11,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpih_b200.so")
 
 PIH_OK, PIH_ERR_INVALID, PIH_ERR_CUDA, PIH_ERR_STATE = 0, -1, -2, -3
-TASK_IDS = {"peg-in-hole": 0, "random-fly": 1}
+TASK_IDS = {"peg-in-hole": 0, "random-fly": 1, "peg-in-hole-scripted": 2}
 ARM_IDS = {"panda": 0, "ur5": 1}
 FLY_OBJECTS = {"banana": 0, "amicelli": 1}
-STATE_F4 = 10
+STATE_F4 = 12
 
 
 class PihConfig(C.Structure):

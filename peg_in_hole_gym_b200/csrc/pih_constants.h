@@ -6,7 +6,7 @@
 
 #define PIH_NB_MAX 9            /* panda: 7 arm + 2 fingers; ur5: 6 */
 #define PIH_MAXC 8              /* contact points kept per env per step (deepest-first) */
-#define PIH_STATE_F4 10         /* float4 slots of env state (layout: DESIGN.md section 4) */
+#define PIH_STATE_F4 12         /* float4 slots of env state (layout: DESIGN.md section 4) */
 #define PIH_STATE_WORDS (4 * PIH_STATE_F4)
 
 /* state word indices inside the [PIH_STATE_F4][N][4] float4-SoA buffer */
@@ -19,6 +19,11 @@
 #define PIH_S_PQUAT 27          /* 27..30 orientation quaternion x,y,z,w */
 #define PIH_S_PVEL 32           /* 32..34 linear velocity */
 #define PIH_S_PANG 35           /* 35..37 angular velocity (env frame) */
+/* scripted grasp task only (envs/peg_in_hole.py:254-267): */
+#define PIH_S_FSM_STATE 21      /* int bits: cur_state 0..9 */
+#define PIH_S_FSM_T 22          /* int bits: engine steps already spent in cur_state (state_t / timeStep) */
+#define PIH_S_RANDY 23          /* random_vector[1] ~ U(-0.03, 0.03) */
+#define PIH_S_MTGT 40           /* 40..46 arm joint position targets that persist between FSM states */
 
 #define PIH_FLAG_DONE 1
 #define PIH_FLAG_SUCCESS 2
@@ -32,6 +37,7 @@
 /* tasks / arms */
 #define PIH_TASK_PEG_IN_HOLE 0
 #define PIH_TASK_RANDOM_FLY 1
+#define PIH_TASK_SCRIPTED 2     /* the scripted grasp->insert state machine the reference ships (peg_in_hole.py:39-225) */
 #define PIH_ARM_PANDA 0
 #define PIH_ARM_UR5 1
 
@@ -80,6 +86,19 @@
 #define PIH_AMICELLI_HX 0.0225
 #define PIH_AMICELLI_HY 0.0212
 #define PIH_AMICELLI_HZ 0.037
+
+/* scripted grasp FSM (envs/peg_in_hole.py:122-212, 254-267) */
+#define PIH_FSM_NSTATES 10
+/* engine steps spent in each state: stateDurations [0.25,2,2,1,1.5,1.5,0.5,0.25,0.25,0.25] s with the reference's
+ * `state_t += 1/240; if state_t > duration` double accumulation (peg_in_hole.py:206-212,263): 2226 steps in total */
+#define PIH_FSM_STEPS_LIST 59, 481, 481, 241, 361, 361, 121, 60, 60, 1
+#define PIH_FSM_DV 0.05                 /* self.dv, peg_in_hole.py:257 */
+#define PIH_FSM_KP 0.1                  /* setJointMotorControl2 default positionGain [3P] */
+#define PIH_FSM_ARM_FORCE (5.0 * 240.0) /* peg_in_hole.py:140,149,164,175,185,200 */
+#define PIH_FSM_FINGER_OPEN 0.02        /* peg_in_hole.py:131,190 (force 20) */
+#define PIH_FSM_FINGER_CLOSED 0.006     /* peg_in_hole.py:154 (force 20000) */
+#define PIH_FSM_FINGER_FORCE_LO 20.0
+#define PIH_FSM_FINGER_FORCE_HI 20000.0
 
 /* RNG stream ids (Philox4x32-10 counter word 2) */
 #define PIH_STREAM_RESET 0

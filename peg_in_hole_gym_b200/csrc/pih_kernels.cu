@@ -119,8 +119,8 @@ template <int ARM> __global__ void __launch_bounds__(128) k_ik(SimParams P, cons
   for (int k = 0; k < A; ++k) a[k] = action[(size_t)A * e + k];
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
-  float qs[nb];
-  apply_action<ARM>(P, S, F, a, env_offset(P, e), qs);
+  float qs[nb], kpc[nb], mfc[nb];
+  apply_action<ARM>(P, S, F, a, env_offset(P, e), qs, kpc, mfc);
 #pragma unroll
   for (int k = 0; k < PIH_NB_MAX; ++k) qtarget[(size_t)PIH_NB_MAX * e + k] = (k < nb) ? qs[k < nb ? k : 0] : 0.0f;
 }
@@ -262,7 +262,7 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   if (!cfg || !out || !state_dev) return PIH_ERR_INVALID;
   *out = nullptr;
   if (cfg->num_envs <= 0 || cfg->sub_num <= 0) return PIH_ERR_INVALID;
-  if (cfg->task != PIH_TASK_PEG_IN_HOLE && cfg->task != PIH_TASK_RANDOM_FLY) return PIH_ERR_INVALID;
+  if (cfg->task != PIH_TASK_PEG_IN_HOLE && cfg->task != PIH_TASK_RANDOM_FLY && cfg->task != PIH_TASK_SCRIPTED) return PIH_ERR_INVALID;
   if (cfg->arm != PIH_ARM_PANDA && cfg->arm != PIH_ARM_UR5) return PIH_ERR_INVALID;
   if (!(cfg->dt > 0.0f) || cfg->solver_iters < 0 || cfg->ik_iters < 0 || !(cfg->solver_residual >= 0.0f)) return PIH_ERR_INVALID;
   // reference assert: task_num == 1 or offset != [0,0,0] (envs/base_env.py:17)

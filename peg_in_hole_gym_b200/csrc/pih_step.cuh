@@ -173,7 +173,7 @@ template <int ARM> PIH_D void collide(const SimParams& P, const EnvState& S, con
     }
   }
   // (2) peg vs annular hole
-  if (P.task == PIH_TASK_PEG_IN_HOLE) {
+  if (P.task != PIH_TASK_RANDOM_FLY) {
     v3 dh = vsub(pfb, mk((float)PIH_HOLE_X, (float)PIH_HOLE_Y, (float)PIH_HOLE_Z));
     const float reach = (float)(PIH_PEG_HL + PIH_PEG_R + PIH_HOLE_ROUT + PIH_HOLE_HL + PIH_CONTACT_MARGIN);
     if (vdot(dh, dh) < reach * reach) {
@@ -279,7 +279,7 @@ template <int ARM> PIH_D void reset_env(const SimParams& P, EnvState& S, unsigne
   rng4(P, gid, (unsigned)S.episode, PIH_STREAM_RESET, u);
 #pragma unroll
   for (int i = 0; i < PIH_NB_MAX; ++i) { S.q[i] = (i < ArmDims<ARM>::NB) ? T.rest[i < ArmDims<ARM>::NB ? i : 0] : 0.0f; S.qd[i] = 0.0f; }
-  if (P.task == PIH_TASK_PEG_IN_HOLE) {
+  if (P.task != PIH_TASK_RANDOM_FLY) {
     S.ppos[0] = fmaf(u[0], 0.4f, -0.2f);
     S.ppos[1] = fmaf(u[1], 0.2f, -0.6f);
     S.ppos[2] = (float)PIH_PEG_SPAWN_Z;
@@ -303,6 +303,10 @@ template <int ARM> PIH_D void reset_env(const SimParams& P, EnvState& S, unsigne
   S.pang[0] = S.pang[1] = S.pang[2] = 0.0f;
   S.step = 0;
   S.flags = 0;
+  S.fsm_state = 0; S.fsm_t = 0;
+  S.rand_y = fmaf(u[3], 0.06f, -0.03f);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) S.mtgt[i] = (i < ArmDims<ARM>::NARM) ? T.rest[i < ArmDims<ARM>::NARM ? i : 0] : 0.0f;
 }
 
 // observation Box(5): [finger1, finger2, EE x, EE y, EE z] in world coordinates (envs/peg_in_hole.py:13)
@@ -317,15 +321,73 @@ template <int ARM> PIH_D void observe(const EnvState& S, v3 off, float (&obs)[5]
   obs[2] = pee.x + off.x; obs[3] = pee.y + off.y; obs[4] = pee.z + off.z;
 }
 
-// apply_action: panda_execute / ur_execute (envs/utils.py:60-82) -> joint position targets
-template <int ARM> PIH_D void apply_action(const SimParams& P, const EnvState& S, const FK<ARM>& F, const float* action, v3 off, float* qstar) {
+// apply_action: panda_execute / ur_execute (envs/utils.py:60-82) -> joint position targets, gains and force caps.
+// Scripted task: apply_action is `pass` (peg_in_hole.py:30-31); the command comes from the grasp state machine
+// (peg_in_hole.py:39-212).  Returns true when the FSM has reached its final state.
+template <int ARM> PIH_D bool apply_action(const SimParams& P, EnvState& S, const FK<ARM>& F, const float* action, v3 off, float* qstar,
+                                           float* kpc, float* mfc) {
   constexpr int nb = ArmDims<ARM>::NB, na = ArmDims<ARM>::NARM;
+  const ArmTables& T = c_arm[ARM];
   v3 pee; m3 Ree;
   ee_pose<ARM>(F, pee, Ree);
-  float ax = action[0], ay = action[1], az = action[2];
-  if (!P.action_frame_env) { ax = ax - off.x; ay = ay - off.y; az = az - off.z; }
+#pragma unroll
+  for (int j = 0; j < nb; ++j) { kpc[j] = T.kp[j]; mfc[j] = T.maxf[j]; }
   v3 tgt;
   float tq[4];
+  if (P.task == PIH_TASK_SCRIPTED) {
+    bool fsm_done = false;
+    const int fsm_steps[PIH_FSM_NSTATES] = {PIH_FSM_STEPS_LIST};
+    int lim = 0;
+#pragma unroll
+    for (int k = 0; k < PIH_FSM_NSTATES; ++k) lim = (S.fsm_state == k) ? fsm_steps[k] : lim;
+    if (S.fsm_t == lim) {
+      S.fsm_state += 1; S.fsm_t = 0;
+      if (S.fsm_state >= PIH_FSM_NSTATES) S.fsm_state = 0;
+    }
+    S.fsm_t += 1;
+    const int st = S.fsm_state;
+    m3 Rp = quat_to_m3(S.pquat);
+    v3 tp = mv_add(Rp, mk(0.0f, S.rand_y, 0.0f), mk(S.ppos[0], S.ppos[1], S.ppos[2]));
+    float qx = S.pquat[0], qy = S.pquat[1], qz = S.pquat[2], qw = S.pquat[3];
+    float yaw = det_atan2(2.0f * fmaf(qx, qy, qw * qz), fmaf(qw, qw, qx * qx) - fmaf(qy, qy, qz * qz));
+    float cur[3] = {pee.x, pee.y, pee.z}, tar[3] = {tp.x, tp.y, tp.z}, res[3];
+    bool arm_cmd = false, clamp = true;
+    float yaw_cmd = 0.0f, zoff = 0.0f;
+    if (st == 1 || st == 2) { arm_cmd = true; yaw_cmd = (float)1.5707963267948966 + yaw; zoff = (st == 1) ? 0.05f : -0.01f; }
+    else if (st == 4 || st == 5 || st == 6) {
+      arm_cmd = true; yaw_cmd = (float)(-3.141592653589793);
+      tar[0] = (float)PIH_HOLE_X - ((st == 4) ? 0.2f : ((st == 5) ? 0.04f : 0.0f));
+      tar[1] = (float)PIH_HOLE_Y; tar[2] = (float)PIH_HOLE_Z;
+      clamp = (st != 6);
+    } else if (st == 8) { arm_cmd = true; yaw_cmd = (float)1.5707963267948966; tar[0] = 0.2f; tar[1] = -0.6f; tar[2] = 0.4f; clamp = false; }
+    else if (st == 9) fsm_done = true;
+    if (arm_cmd) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        float diff = tar[i] - cur[i];
+        if (clamp && fabsf(diff) > (float)PIH_FSM_DV) res[i] = cur[i] + ((diff > 0.0f) ? (float)PIH_FSM_DV : (float)(-PIH_FSM_DV));
+        else res[i] = cur[i] + diff;
+      }
+      tgt = mk(res[0], res[1], res[2] + zoff);
+      euler_to_quat(0.0f, (float)(-3.141592653589793), yaw_cmd, tq);
+      float qik[nb];
+      ik_dls<ARM>(P, F, S.q, tgt, tq, qik);
+#pragma unroll
+      for (int j = 0; j < na && j < 7; ++j) S.mtgt[j] = qik[j];
+    }
+#pragma unroll
+    for (int j = 0; j < na; ++j) { qstar[j] = S.mtgt[j < 7 ? j : 0]; kpc[j] = (float)PIH_FSM_KP; mfc[j] = (float)PIH_FSM_ARM_FORCE; }
+    const bool closed = (st >= 3 && st <= 6);
+#pragma unroll
+    for (int j = na; j < nb; ++j) {
+      qstar[j] = closed ? (float)PIH_FSM_FINGER_CLOSED : (float)PIH_FSM_FINGER_OPEN;
+      kpc[j] = (float)PIH_FSM_KP;
+      mfc[j] = closed ? (float)PIH_FSM_FINGER_FORCE_HI : (float)PIH_FSM_FINGER_FORCE_LO;
+    }
+    return fsm_done;
+  }
+  float ax = action[0], ay = action[1], az = action[2];
+  if (!P.action_frame_env) { ax = ax - off.x; ay = ay - off.y; az = az - off.z; }
   if (ARM == PIH_ARM_PANDA) {
     float cur[3] = {pee.x, pee.y, pee.z}, tar[3] = {ax, ay, az}, res[3];
 #pragma unroll
@@ -343,6 +405,7 @@ template <int ARM> PIH_D void apply_action(const SimParams& P, const EnvState& S
   ik_dls<ARM>(P, F, S.q, tgt, tq, qstar);
 #pragma unroll
   for (int j = na; j < nb; ++j) qstar[j] = action[3];
+  return false;
 }
 
 // One env.step for one env.  Returns false if the env was frozen (done and not reset): outputs untouched.
@@ -354,8 +417,8 @@ template <int ARM> __device__ __noinline__ bool step_env(const SimParams& P, Env
   const float dt = P.dt, idt = P.idt;
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
-  float qstar[nb];
-  apply_action<ARM>(P, S, F, action, off, qstar);
+  float qstar[nb], kpc[nb], mfc[nb];
+  const bool fsm_done = apply_action<ARM>(P, S, F, action, off, qstar, kpc, mfc);
   // ---- unconstrained accelerations
   float tau[nb];
 #pragma unroll
@@ -398,11 +461,11 @@ template <int ARM> __device__ __noinline__ bool step_env(const SimParams& P, Env
     // targets outside the URDF limits are unreachable: aim at the limit instead of fighting the limit row
     float qt = qstar[j];
     qt = (qt < T.lo[j]) ? T.lo[j] : ((qt > T.hi[j]) ? T.hi[j] : qt);
-    float vstar = T.kp[j] * (qt - S.q[j]) * idt;
+    float vstar = kpc[j] * (qt - S.q[j]) * idt;
     m_dinv[j] = 1.0f / Minv[j][j];
     m_b[j] = (vstar - vs[j]) * m_dinv[j];
     m_lam[j] = 0.0f;
-    m_max[j] = T.maxf[j] * dt;
+    m_max[j] = mfc[j] * dt;
     // a limit row exists only if the joint can reach that limit this step (see oracle for the rule)
     float glo = S.q[j] - T.lo[j], ghi = T.hi[j] - S.q[j];
     float vdn = fmaxf(fmaxf(-vstar, -vs[j]), 0.0f), vup = fmaxf(fmaxf(vstar, vs[j]), 0.0f);
@@ -616,7 +679,7 @@ template <int ARM> __device__ __noinline__ bool step_env(const SimParams& P, Env
   v3 pee2; m3 Ree2;
   fk<ARM, nb>(S.q, F2);
   ee_pose<ARM>(F2, pee2, Ree2);
-  if (P.task == PIH_TASK_PEG_IN_HOLE) {
+  if (P.task != PIH_TASK_RANDOM_FLY) {
     v3 d = mk(S.ppos[0] - (float)PIH_HOLE_X, S.ppos[1] - (float)PIH_HOLE_Y, S.ppos[2] - (float)PIH_HOLE_Z);
     success = vdot(d, d) < (float)(PIH_SUCCESS_RADIUS * PIH_SUCCESS_RADIUS);
   } else {
@@ -626,6 +689,7 @@ template <int ARM> __device__ __noinline__ bool step_env(const SimParams& P, Env
   rew = success ? 1.0f : 0.0f;
   int dn = success || (P.max_steps > 0 && S.step >= P.max_steps);
   if (P.task == PIH_TASK_RANDOM_FLY && (pairmask & PIH_PAIR_PEG_TABLE)) dn = 1;
+  if (P.task == PIH_TASK_SCRIPTED) dn = fsm_done || (P.max_steps > 0 && S.step >= P.max_steps);
   S.flags = (dn ? PIH_FLAG_DONE : 0) | (success ? PIH_FLAG_SUCCESS : 0) | (pairmask << PIH_PAIR_SHIFT);
   reward = rew;
   done = (unsigned char)dn;

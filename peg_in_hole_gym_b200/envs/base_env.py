@@ -8,13 +8,14 @@ import torch
 
 from .. import gym_shim as gym
 from ..sim import BatchedSim
-from .peg_in_hole import PegInHole, PegInHoleUR5
+from .peg_in_hole import PegInHole, PegInHoleScripted, PegInHoleUR5
 from .random_fly import RandomFly
 from .utils import MultiAgentActionSpace, MultiAgentObservationSpace, test_mode
 
 TASK_LIST = {
     'peg-in-hole': PegInHole,      # base_env.py:9-11
     'peg-in-hole-ur5': PegInHoleUR5,
+    'peg-in-hole-scripted': PegInHoleScripted,   # the scripted grasp FSM the reference ships (peg_in_hole.py:39-225)
     'random-fly': RandomFly,       # README.md:38 (source missing from the snapshot; NEW semantics)
 }
 
@@ -98,7 +99,7 @@ class BaseEnv(gym.Env):
             raise AttributeError("step() called before reset()")  # reference: no self.dones yet (base_env.py:62)
         a = _to_action_tensor(action, self.sim.n, self.sim.action_dim, self.sim.device)
         a = self.plugin.apply_action(a)
-        self.sim.step(a)
+        self.plugin.native_step(a)
         obs, reward, done, _ = self.plugin.get_info()
         if self.is_test:
             test_mode('r', self.reset)

@@ -48,6 +48,10 @@ class MetaEnv(object):
     def apply_action(self, action):
         return action
 
+    def native_step(self, action):
+        """One engine step of every sub-env (BaseEnv.step's single stepSimulation, base_env.py:64)."""
+        self.p.step(action)
+
     def get_info(self):
         return self.p.obs, self.p.reward, self.p.done, None
 

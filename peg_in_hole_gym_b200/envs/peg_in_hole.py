@@ -31,3 +31,23 @@ class PegInHoleUR5(PegInHole):
     """ur5 arm variant (envs/utils.py:40-48,70-82): 6-D action = absolute position + Euler orientation (NEW Box)."""
     action_space = spaces.Box(np.array([-1] * 6), np.array([1] * 6))
     arm = "ur5"
+
+
+class PegInHoleScripted(PegInHole):
+    """The task exactly as the reference ships it (peg_in_hole.py:30-37): ``apply_action`` is a no-op and one
+    ``step()`` runs the whole scripted grasp -> lift -> insert -> release episode (10 timed states, 2226 engine
+    steps of 1/240 s) and returns the success reward of peg_in_hole.py:114-117.  The state machine runs inside the
+    rollout kernel; the observation is the 5-vector (the camera image of peg_in_hole.py:66-98 is SURVEY 8f rank 3).
+    Differences flagged NEW: rigid peg segment instead of the 25-link pipe; the JOINT_GEAR grasp constraint
+    (peg_in_hole.py:99-104) is replaced by the friction grasp alone."""
+    native_task = "peg-in-hole-scripted"
+    EPISODE_STEPS = 2226
+
+    def sim_config(self):
+        return dict(task="peg-in-hole-scripted", arm="panda", dt=1.0 / 240.0)
+
+    def apply_action(self, action):      # peg_in_hole.py:30-31
+        return action
+
+    def native_step(self, action):       # get_info -> random_grasp(): `while not done` loop (peg_in_hole.py:52-112)
+        self.p.rollout(self.EPISODE_STEPS, count=False)

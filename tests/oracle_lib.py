@@ -82,8 +82,9 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-STATE_WORDS = 40
+STATE_WORDS = 48
 S_Q, S_STEP, S_EPISODE, S_FLAGS, S_QD, S_PPOS, S_PQUAT, S_PVEL, S_PANG = 0, 9, 10, 11, 12, 24, 27, 32, 35
+S_FSM_STATE, S_FSM_T, S_RANDY, S_MTGT = 21, 22, 23, 40
 
 
 class Oracle:

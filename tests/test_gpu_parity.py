@@ -295,3 +295,27 @@ def test_gym_surface_end_to_end():
     o, r, d, i = env.step(env.action_space.sample())
     assert isinstance(o, list) and len(o) == 4 and len(o[0]) == 5 and isinstance(i[0], dict)
     env.close()
+
+
+def test_scripted_grasp_fsm_bit_exact_and_through_gym_surface():
+    """the scripted state machine, 2226 engine steps, CUDA vs oracle bit for bit."""
+    n = 32
+    sim, orc = _pair(n, task="peg-in-hole", offset=(2.0, 3.0, 0.0), seed=3)
+    sim.close()
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    sim = BatchedSim(n, task="peg-in-hole-scripted", offset=(2.0, 3.0, 0.0), seed=3, device=0)
+    orc = ol.Oracle(ol.make_config(n, task=2, offset=(2.0, 3.0, 0.0), seed=3))
+    assert np.array_equal(sim.reset().cpu().numpy(), orc.reset())
+    for chunk in (500, 800, 926):
+        sim.rollout(chunk)
+        orc.rollout(chunk)
+        _assert_state_equal(sim, orc)
+    assert sim.done.cpu().numpy().all() and np.array_equal(sim.reward.cpu().numpy(), orc.reward)
+    assert ((sim.int_word(11).cpu().numpy() >> 8) & 0xff).any()
+    import peg_in_hole_gym_b200 as gym
+    env = gym.make('peg-in-hole-mp-v0', client=gym.DIRECT, task='peg-in-hole-scripted', mp_num=2, sub_num=16, offset=[2., 3., 0.],
+                   seed=3, shard=False)
+    env.reset()
+    obs, reward, done, info = env.step(env.action_space.sample_array())      # one step() = one scripted episode
+    assert bool(done.all()) and np.array_equal(reward.cpu().numpy().ravel(), orc.reward)
+    env.close()

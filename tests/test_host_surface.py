@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     from peg_in_hole_gym_b200 import _native
     assert set(_native.EXPORTS) == declared
     LL = _native.lib()
-    assert LL.pih_abi_version() == 1 and LL.pih_state_words() == 40 and LL.pih_obs_dim() == 5
+    assert LL.pih_abi_version() == 1 and LL.pih_state_words() == 48 and LL.pih_obs_dim() == 5
     assert LL.pih_action_dim(0) == 4 and LL.pih_action_dim(1) == 6 and LL.pih_action_dim(7) < 0
 
 

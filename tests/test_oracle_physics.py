@@ -176,3 +176,25 @@ def test_oracle_reproduces_golden_fixtures(case):
         assert np.array_equal(d, g["done"][t]) and np.array_equal(r, g["reward"][t]), t
         assert np.allclose(obs, g["obs"][t], atol=1e-6), t
     assert np.allclose(o.get_state(), g["state"], atol=1e-6)
+
+
+def test_scripted_grasp_fsm_runs_the_reference_schedule():
+    """peg_in_hole.py:206-212,263: 10 timed states, 2226 engine steps; the episode ends in state 9; the scripted
+    pick-and-insert succeeds for part of the envs (friction grasp of the rigid peg stand-in)."""
+    n = 12
+    o = ol.Oracle(ol.make_config(n, task=2, offset=(2.0, 3.0, 0.0), seed=3), use_double=True)
+    o.reset()
+    a = np.zeros((n, 4), np.float32)
+    counts = np.zeros(10, int)
+    seen_hole = False
+    for t in range(2300):
+        obs, r, d = o.step(a)
+        w = o.get_state()
+        if d.all():
+            break
+        counts[ol.state_int(w, ol.S_FSM_STATE)[0]] += 1
+        seen_hole = seen_hole or bool(((ol.state_int(w, ol.S_FLAGS) >> 8) & 2).any())
+    assert t + 1 == 2226 and list(counts) == [59, 481, 481, 241, 361, 361, 121, 60, 60, 0]
+    assert np.isfinite(w).all() and seen_hole
+    assert r.mean() >= 0.25                           # some pegs end within 5 cm of the hole (peg_in_hole.py:114-117)
+    assert np.allclose(obs[:, 2:5] - np.array([[2.0 * (i // 4), 3.0 * (i % 4), 0.0] for i in range(n)]), [0.2, -0.6, 0.4], atol=0.02)
