@@ -37,7 +37,7 @@ MAX_STEPS = 200
 OFFSET = (2.0, 3.0, 0.0)   # README.md:38
 SEED = 0
 # algorithmic cost per env-step (SURVEY.md 8d formula)
-BYTES_PER_ENV_STEP = 2 * 160 + 16 + 20 + 4 + 1   # float4-SoA state read+write (10 slots), action, obs, reward, done
+BYTES_PER_ENV_STEP = 2 * 192 + 16 + 20 + 4 + 1   # float4-SoA state read+write (12 slots), action, obs, reward, done
 FLOPS_BULLET_DEFAULT = 2.2e5                       # I_ik=20, I_pgs=50, n=9, R=33
 NCU_TRAFFIC_BYTES = 922368                         # k_step<panda>, 4096 envs: DRAM read 922 KB + write 0 B per launch (profiles/)
 

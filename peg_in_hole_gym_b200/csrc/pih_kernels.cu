@@ -15,14 +15,14 @@ namespace pih {
 // ------------------------------------------------------------------------------------------------ kernels
 // thread-per-env; grid = ceil(n / blockDim).  State is read once and written once per launch as float4 SoA.
 
-template <int ARM> __global__ void __launch_bounds__(128) k_reset(SimParams P, const unsigned char* __restrict__ mask, float* __restrict__ obs) {
+template <int ARM, int TASK> __global__ void __launch_bounds__(128) k_reset(SimParams P, const unsigned char* __restrict__ mask, float* __restrict__ obs) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.n) return;
   if (mask && !mask[e]) return;
   EnvState S;
   load_state(P, e, S);
   S.episode += 1;
-  reset_env<ARM>(P, S, (unsigned)(P.env_id_base + e));
+  reset_env<ARM, TASK>(P, S, (unsigned)(P.env_id_base + e));
   store_state(P, e, S);
   if (obs) {
     float o[5];
@@ -32,7 +32,7 @@ template <int ARM> __global__ void __launch_bounds__(128) k_reset(SimParams P, c
   }
 }
 
-template <int ARM> __global__ void __launch_bounds__(128) k_step(SimParams P, const float* __restrict__ action, float* __restrict__ obs,
+template <int ARM, int TASK> __global__ void __launch_bounds__(128) k_step(SimParams P, const float* __restrict__ action, float* __restrict__ obs,
                                                                 float* __restrict__ reward, unsigned char* __restrict__ done) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.n) return;
@@ -49,7 +49,7 @@ template <int ARM> __global__ void __launch_bounds__(128) k_step(SimParams P, co
   }
   float o[5], r;
   unsigned char d;
-  if (!step_env<ARM>(P, S, a, env_offset(P, e), (unsigned)(P.env_id_base + e), o, r, d)) return;  // frozen: keep outputs
+  if (!step_env<ARM, TASK>(P, S, a, env_offset(P, e), (unsigned)(P.env_id_base + e), o, r, d)) return;  // frozen: keep outputs
   store_state(P, e, S);
   if (obs) {
 #pragma unroll
@@ -59,7 +59,7 @@ template <int ARM> __global__ void __launch_bounds__(128) k_step(SimParams P, co
   if (done) done[e] = d;
 }
 
-template <int ARM> __global__ void __launch_bounds__(128) k_rollout(SimParams P, int steps, float* __restrict__ obs, float* __restrict__ reward,
+template <int ARM, int TASK> __global__ void __launch_bounds__(128) k_rollout(SimParams P, int steps, float* __restrict__ obs, float* __restrict__ reward,
                                                                    unsigned char* __restrict__ done, unsigned long long* __restrict__ counters) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.n) return;
@@ -83,7 +83,7 @@ template <int ARM> __global__ void __launch_bounds__(128) k_rollout(SimParams P,
     if (!P.action_frame_env) { a[0] += off.x; a[1] += off.y; a[2] += off.z; }
     float o2[5], r2;
     unsigned char d2;
-    if (step_env<ARM>(P, S, a, off, gid, o2, r2, d2)) {
+    if (step_env<ARM, TASK>(P, S, a, off, gid, o2, r2, d2)) {
       any = true;
 #pragma unroll
       for (int k = 0; k < 5; ++k) o[k] = o2[k];
@@ -108,7 +108,7 @@ template <int ARM> __global__ void __launch_bounds__(128) k_rollout(SimParams P,
   }
 }
 
-template <int ARM> __global__ void __launch_bounds__(128) k_ik(SimParams P, const float* __restrict__ action, float* __restrict__ qtarget) {
+template <int ARM, int TASK> __global__ void __launch_bounds__(128) k_ik(SimParams P, const float* __restrict__ action, float* __restrict__ qtarget) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.n) return;
   constexpr int A = ArmDims<ARM>::ADIM, nb = ArmDims<ARM>::NB;
@@ -120,7 +120,7 @@ template <int ARM> __global__ void __launch_bounds__(128) k_ik(SimParams P, cons
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
   float qs[nb], kpc[nb], mfc[nb];
-  apply_action<ARM>(P, S, F, a, env_offset(P, e), qs, kpc, mfc);
+  apply_action<ARM, TASK>(P, S, F, a, env_offset(P, e), qs, kpc, mfc);
 #pragma unroll
   for (int k = 0; k < PIH_NB_MAX; ++k) qtarget[(size_t)PIH_NB_MAX * e + k] = (k < nb) ? qs[k < nb ? k : 0] : 0.0f;
 }
@@ -335,11 +335,23 @@ void pih_destroy(pih_handle* h) {
 
 const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null handle"; }
 
-#define LAUNCH(kern, h, st, ...)                                                               \
-  do {                                                                                         \
-    int grid_ = ((h)->P.n + (h)->block - 1) / (h)->block;                                      \
+#define LAUNCH_T(kern, ARMV, h, st, ...)                                                                                \
+  do {                                                                                                                 \
+    if ((h)->P.task == PIH_TASK_PEG_IN_HOLE) kern<ARMV, PIH_TASK_PEG_IN_HOLE><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
+    else if ((h)->P.task == PIH_TASK_RANDOM_FLY) kern<ARMV, PIH_TASK_RANDOM_FLY><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
+    else kern<ARMV, PIH_TASK_SCRIPTED><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__);                     \
+  } while (0)
+#define LAUNCH(kern, h, st, ...)                                                  \
+  do {                                                                            \
+    int grid_ = ((h)->P.n + (h)->block - 1) / (h)->block;                         \
+    if ((h)->P.arm == PIH_ARM_PANDA) LAUNCH_T(kern, PIH_ARM_PANDA, h, st, __VA_ARGS__); \
+    else LAUNCH_T(kern, PIH_ARM_UR5, h, st, __VA_ARGS__);                         \
+  } while (0)
+#define LAUNCH_ARM(kern, h, st, ...)                                              \
+  do {                                                                            \
+    int grid_ = ((h)->P.n + (h)->block - 1) / (h)->block;                         \
     if ((h)->P.arm == PIH_ARM_PANDA) kern<PIH_ARM_PANDA><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
-    else kern<PIH_ARM_UR5><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__);          \
+    else kern<PIH_ARM_UR5><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
   } while (0)
 
 int pih_reset(pih_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
@@ -423,7 +435,7 @@ int pih_ik_targets(pih_handle* h, const float* action_dev, float* qtarget_dev, v
 
 int pih_ee_pose(pih_handle* h, float* pos_dev, float* rot_dev, void* stream) {
   if (!h) return PIH_ERR_INVALID;
-  LAUNCH(k_ee, h, stream, h->P, pos_dev, rot_dev);
+  LAUNCH_ARM(k_ee, h, stream, h->P, pos_dev, rot_dev);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_ee launch", ce);
   return PIH_OK;

@@ -72,11 +72,11 @@ PIH_D float sd_box(v3 l, v3 h, v3& nl) {
   return d;
 }
 
-PIH_D float fb_sdf(const SimParams& P, const m3& R, v3 p, v3 x, v3& n_env) {
+template <int TASK> PIH_D float fb_sdf(const SimParams& P, const m3& R, v3 p, v3 x, v3& n_env) {
   v3 l = mTv(R, vsub(x, p));
   v3 nl;
   float d;
-  if (P.fb_shape == 0) {
+  if ((TASK != PIH_TASK_RANDOM_FLY)) {
     float rho = sqrtf(fmaf(l.z, l.z, l.x * l.x));
     float da = rho - P.fb_half[0], db = fabsf(l.y) - P.fb_half[1];
     float na, nb_;
@@ -111,8 +111,8 @@ PIH_D void circ8(int k, float& c, float& s) {
   s = (kk == 2) ? 1.0f : (kk == 6) ? -1.0f : (kk == 0 || kk == 4) ? 0.0f : (kk == 1 || kk == 3) ? h : -h;
 }
 
-PIH_D bool fb_sample(const SimParams& P, int k, v3& pl) {
-  if (P.fb_shape == 0) {
+template <int TASK> PIH_D bool fb_sample(const SimParams& P, int k, v3& pl) {
+  if ((TASK != PIH_TASK_RANDOM_FLY)) {
     float c, s;
     circ8(k, c, s);
     float sy = (k < 8) ? 1.0f : -1.0f;
@@ -124,7 +124,7 @@ PIH_D bool fb_sample(const SimParams& P, int k, v3& pl) {
   return true;
 }
 
-template <int ARM> PIH_D void collide(const SimParams& P, const EnvState& S, const FK<ARM>& F, const m3& Rfb, ContactSet& CS) {
+template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvState& S, const FK<ARM>& F, const m3& Rfb, ContactSet& CS) {
   const ArmTables& T = c_arm[ARM];
   CS.n = 0;
   v3 pfb = mk(S.ppos[0], S.ppos[1], S.ppos[2]);
@@ -132,7 +132,7 @@ template <int ARM> PIH_D void collide(const SimParams& P, const EnvState& S, con
   const float mu_static = P.fb_mu * (float)PIH_MU_DEFAULT;
   // (1) free body vs table plane
   if (pfb.z - (float)PIH_TABLE_Z < 0.25f) {  // cheap cull: nothing of the body is near the table (exact no-op otherwise)
-    if (P.fb_shape == 0) {
+    if ((TASK != PIH_TASK_RANDOM_FLY)) {
       v3 ax = mcol(Rfb, 1);
       float naz = ax.z;
       v3 nperp = mk(-(naz * ax.x), -(naz * ax.y), fmaf(-naz, ax.z, 1.0f));
@@ -164,7 +164,7 @@ template <int ARM> PIH_D void collide(const SimParams& P, const EnvState& S, con
     } else {
       for (int k = 0; k < 8; ++k) {
         v3 pl;
-        fb_sample(P, k, pl);
+        fb_sample<TASK>(P, k, pl);
         v3 pt = mv_add(Rfb, pl, pfb);
         c.pair = PIH_PAIR_PEG_TABLE; c.has_fb = 1; c.arm_body = -1; c.p = pt; c.n = mk(0.0f, 0.0f, 1.0f);
         c.dist = pt.z - (float)PIH_TABLE_Z; c.mu = mu_static;
@@ -173,13 +173,13 @@ template <int ARM> PIH_D void collide(const SimParams& P, const EnvState& S, con
     }
   }
   // (2) peg vs annular hole
-  if (P.task != PIH_TASK_RANDOM_FLY) {
+  if (TASK != PIH_TASK_RANDOM_FLY) {
     v3 dh = vsub(pfb, mk((float)PIH_HOLE_X, (float)PIH_HOLE_Y, (float)PIH_HOLE_Z));
     const float reach = (float)(PIH_PEG_HL + PIH_PEG_R + PIH_HOLE_ROUT + PIH_HOLE_HL + PIH_CONTACT_MARGIN);
     if (vdot(dh, dh) < reach * reach) {
       for (int k = 0; k < 16; ++k) {
         v3 pl, nn;
-        fb_sample(P, k, pl);
+        fb_sample<TASK>(P, k, pl);
         v3 pt = mv_add(Rfb, pl, pfb);
         float d = hole_sdf(pt, nn);
         c.pair = PIH_PAIR_PEG_HOLE; c.has_fb = 1; c.arm_body = -1; c.p = pt; c.n = nn; c.dist = d; c.mu = mu_static;
@@ -192,7 +192,7 @@ template <int ARM> PIH_D void collide(const SimParams& P, const EnvState& S, con
         circ8(k, cc, ss);
         v3 pt = mk((float)PIH_HOLE_X + sx, fmaf(rr, cc, (float)PIH_HOLE_Y), fmaf(rr, ss, (float)PIH_HOLE_Z));
         v3 nn;
-        float d = fb_sdf(P, Rfb, pfb, pt, nn);
+        float d = fb_sdf<TASK>(P, Rfb, pfb, pt, nn);
         c.pair = PIH_PAIR_PEG_HOLE; c.has_fb = 1; c.arm_body = -1; c.p = pt; c.n = mk(-nn.x, -nn.y, -nn.z); c.dist = d; c.mu = mu_static;
         contact_push(CS, c);
       }
@@ -208,12 +208,12 @@ template <int ARM> PIH_D void collide(const SimParams& P, const EnvState& S, con
     float reach = P.fb_half[1] + P.fb_half[0] + T.box_h[b][2] + T.box_h[b][0] + (float)PIH_CONTACT_MARGIN;
     if (!(vdot(dd, dd) < reach * reach)) continue;
     m3 Rb = mmul(F.Rw[body], ldm(T.box_R[b]));
-    int npts = (P.fb_shape == 0) ? 5 : 8;
+    int npts = ((TASK != PIH_TASK_RANDOM_FLY)) ? 5 : 8;
     for (int k = 0; k < npts; ++k) {
       v3 pl;
       float rad;
-      if (P.fb_shape == 0) { pl = mk(0.0f, (P.fb_half[1] - P.fb_half[0]) * 0.5f * (float)(k - 2), 0.0f); rad = P.fb_half[0]; }
-      else { fb_sample(P, k, pl); rad = 0.0f; }
+      if ((TASK != PIH_TASK_RANDOM_FLY)) { pl = mk(0.0f, (P.fb_half[1] - P.fb_half[0]) * 0.5f * (float)(k - 2), 0.0f); rad = P.fb_half[0]; }
+      else { fb_sample<TASK>(P, k, pl); rad = 0.0f; }
       v3 pt = mv_add(Rfb, pl, pfb);
       v3 l = mTv(Rb, vsub(pt, cb));
       v3 nl;
@@ -273,13 +273,13 @@ template <int ARM> PIH_D unsigned anc_rt(int body) {
 }
 
 // PegInHole.reset distributions (envs/peg_in_hole.py:233-245) with Philox (seed; env id, episode)
-template <int ARM> PIH_D void reset_env(const SimParams& P, EnvState& S, unsigned gid) {
+template <int ARM, int TASK> PIH_D void reset_env(const SimParams& P, EnvState& S, unsigned gid) {
   const ArmTables& T = c_arm[ARM];
   float u[4];
   rng4(P, gid, (unsigned)S.episode, PIH_STREAM_RESET, u);
 #pragma unroll
   for (int i = 0; i < PIH_NB_MAX; ++i) { S.q[i] = (i < ArmDims<ARM>::NB) ? T.rest[i < ArmDims<ARM>::NB ? i : 0] : 0.0f; S.qd[i] = 0.0f; }
-  if (P.task != PIH_TASK_RANDOM_FLY) {
+  if (TASK != PIH_TASK_RANDOM_FLY) {
     S.ppos[0] = fmaf(u[0], 0.4f, -0.2f);
     S.ppos[1] = fmaf(u[1], 0.2f, -0.6f);
     S.ppos[2] = (float)PIH_PEG_SPAWN_Z;
@@ -324,7 +324,7 @@ template <int ARM> PIH_D void observe(const EnvState& S, v3 off, float (&obs)[5]
 // apply_action: panda_execute / ur_execute (envs/utils.py:60-82) -> joint position targets, gains and force caps.
 // Scripted task: apply_action is `pass` (peg_in_hole.py:30-31); the command comes from the grasp state machine
 // (peg_in_hole.py:39-212).  Returns true when the FSM has reached its final state.
-template <int ARM> PIH_D bool apply_action(const SimParams& P, EnvState& S, const FK<ARM>& F, const float* action, v3 off, float* qstar,
+template <int ARM, int TASK> PIH_D bool apply_action(const SimParams& P, EnvState& S, const FK<ARM>& F, const float* action, v3 off, float* qstar,
                                            float* kpc, float* mfc) {
   constexpr int nb = ArmDims<ARM>::NB, na = ArmDims<ARM>::NARM;
   const ArmTables& T = c_arm[ARM];
@@ -334,7 +334,7 @@ template <int ARM> PIH_D bool apply_action(const SimParams& P, EnvState& S, cons
   for (int j = 0; j < nb; ++j) { kpc[j] = T.kp[j]; mfc[j] = T.maxf[j]; }
   v3 tgt;
   float tq[4];
-  if (P.task == PIH_TASK_SCRIPTED) {
+  if (TASK == PIH_TASK_SCRIPTED) {
     bool fsm_done = false;
     const int fsm_steps[PIH_FSM_NSTATES] = {PIH_FSM_STEPS_LIST};
     int lim = 0;
@@ -409,7 +409,7 @@ template <int ARM> PIH_D bool apply_action(const SimParams& P, EnvState& S, cons
 }
 
 // One env.step for one env.  Returns false if the env was frozen (done and not reset): outputs untouched.
-template <int ARM> __device__ __noinline__ bool step_env(const SimParams& P, EnvState& S, const float* action, v3 off, unsigned gid,
+template <int ARM, int TASK> __device__ __noinline__ bool step_env(const SimParams& P, EnvState& S, const float* action, v3 off, unsigned gid,
                                                          float (&obs)[5], float& reward, unsigned char& done) {
   if (S.flags & PIH_FLAG_DONE) return false;
   constexpr int nb = ArmDims<ARM>::NB, na = ArmDims<ARM>::NARM;
@@ -418,7 +418,7 @@ template <int ARM> __device__ __noinline__ bool step_env(const SimParams& P, Env
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
   float qstar[nb], kpc[nb], mfc[nb];
-  const bool fsm_done = apply_action<ARM>(P, S, F, action, off, qstar, kpc, mfc);
+  const bool fsm_done = apply_action<ARM, TASK>(P, S, F, action, off, qstar, kpc, mfc);
   // ---- unconstrained accelerations
   float tau[nb];
 #pragma unroll
@@ -479,7 +479,7 @@ template <int ARM> __device__ __noinline__ bool step_env(const SimParams& P, Env
   }
   // ---- contacts
   ContactSet CS;
-  collide<ARM>(P, S, F, Rfb, CS);
+  collide<ARM, TASK>(P, S, F, Rfb, CS);
   CRow<ARM> rows[PIH_MAXC];
   int pairmask = 0;
   bool arm_contacts = false;
@@ -679,7 +679,7 @@ template <int ARM> __device__ __noinline__ bool step_env(const SimParams& P, Env
   v3 pee2; m3 Ree2;
   fk<ARM, nb>(S.q, F2);
   ee_pose<ARM>(F2, pee2, Ree2);
-  if (P.task != PIH_TASK_RANDOM_FLY) {
+  if (TASK != PIH_TASK_RANDOM_FLY) {
     v3 d = mk(S.ppos[0] - (float)PIH_HOLE_X, S.ppos[1] - (float)PIH_HOLE_Y, S.ppos[2] - (float)PIH_HOLE_Z);
     success = vdot(d, d) < (float)(PIH_SUCCESS_RADIUS * PIH_SUCCESS_RADIUS);
   } else {
@@ -688,15 +688,15 @@ template <int ARM> __device__ __noinline__ bool step_env(const SimParams& P, Env
   }
   rew = success ? 1.0f : 0.0f;
   int dn = success || (P.max_steps > 0 && S.step >= P.max_steps);
-  if (P.task == PIH_TASK_RANDOM_FLY && (pairmask & PIH_PAIR_PEG_TABLE)) dn = 1;
-  if (P.task == PIH_TASK_SCRIPTED) dn = fsm_done || (P.max_steps > 0 && S.step >= P.max_steps);
+  if (TASK == PIH_TASK_RANDOM_FLY && (pairmask & PIH_PAIR_PEG_TABLE)) dn = 1;
+  if (TASK == PIH_TASK_SCRIPTED) dn = fsm_done || (P.max_steps > 0 && S.step >= P.max_steps);
   S.flags = (dn ? PIH_FLAG_DONE : 0) | (success ? PIH_FLAG_SUCCESS : 0) | (pairmask << PIH_PAIR_SHIFT);
   reward = rew;
   done = (unsigned char)dn;
   if (dn && P.auto_reset) {
     int keep = S.flags & ~PIH_FLAG_DONE;
     S.episode += 1;
-    reset_env<ARM>(P, S, gid);
+    reset_env<ARM, TASK>(P, S, gid);
     S.flags = keep & ~0xff;
     observe<ARM>(S, off, obs);
   } else {
