@@ -94,6 +94,11 @@ int pih_ik_targets(pih_handle* h, const float* action_dev, float* qtarget_dev, v
 /* getLinkState(ee)[0:2] for every env (utils.py:62-63): pos float[num_envs][3] (world), rot float[num_envs][9]. */
 int pih_ee_pose(pih_handle* h, float* pos_dev, float* rot_dev, void* stream);
 
+/* PegInHole.render (peg_in_hole.py:276-304) for every env: camera at the end effector looking along -z, FOV 60 deg,
+ * near 0.001, far 1000.  rgbd_dev float[num_envs][height][width][4] = (OpenGL depth buffer value, r, g, b in 0..255),
+ * the layout of the reference's np.concatenate((depth, rgb), 2).  The reference renders 300 x 300. */
+int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, void* stream);
+
 /* FP32 FMA-throughput micro-benchmark (roofline denominator): returns measured TFLOP/s. */
 int pih_measure_fp32_peak(int device, double* tflops_out);
 

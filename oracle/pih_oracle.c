@@ -333,3 +333,19 @@ int pih_oracle_model_nb(int arm) { return arm == PIH_ARM_PANDA ? PIH_PANDA_NB : 
 
 void pih_oracle_sincos(float x, float* s, float* c) { pih_sincosf_det(x, s, c); }
 float pih_oracle_atan2_q1(float y, float x) { return det_atan2_q1_f(y, x); }
+
+/* PegInHole.render for envs [lo, hi): out float[hi-lo][H][W][4] = (depth, r, g, b) */
+int pih_oracle_render(void* h, int W, int H, int lo, int hi, float* out) {
+  oracle* o = (oracle*)h;
+  for (int i = lo; i < hi; ++i) {
+    float* dst = out + (size_t)(i - lo) * H * W * 4;
+    if (o->use_double) {
+      scene_d SC; build_scene_d(&o->md, &o->sd[i], &SC);
+      for (int r = 0; r < H; ++r) for (int c = 0; c < W; ++c) render_pixel_d(&o->md, &o->cd, &SC, r, c, W, H, dst + ((size_t)r * W + c) * 4);
+    } else {
+      scene_f SC; build_scene_f(&o->mf, &o->sf[i], &SC);
+      for (int r = 0; r < H; ++r) for (int c = 0; c < W; ++c) render_pixel_f(&o->mf, &o->cf, &SC, r, c, W, H, dst + ((size_t)r * W + c) * 4);
+    }
+  }
+  return 0;
+}

@@ -942,6 +942,166 @@ static void FN(observe)(const model* M, const simcfg* C, const envstate* S, cons
   obs[2] = pee.x + off[0]; obs[3] = pee.y + off[1]; obs[4] = pee.z + off[2];
 }
 
+
+/* ------------------------------------------------------------------ camera (PegInHole.render, peg_in_hole.py:276-304)
+ * Ray caster over the same analytic primitives the contact code uses: table plane, free body (capped cylinder or
+ * box), annular hole, finger boxes.  TinyRenderer itself is [3P] and not restated; what is kept is the camera model
+ * (computeViewMatrix eye=EE, target=EE-(0,0,10), up=(0,1,0); computeProjectionMatrixFOV 60/1/0.001/1000), the
+ * 300x300x4 (depth, r, g, b) layout and the OpenGL depth-buffer encoding.  Colours / flat Lambert shading are NEW. */
+typedef struct {
+  v3 eye;
+  m3 Rfb; v3 pfb;
+  m3 Rbox[PIH_MAX_BOX]; v3 cbox[PIH_MAX_BOX];
+} FN(scene);
+#define scene FN(scene)
+
+static void FN(build_scene)(const model* M, const envstate* S, scene* SC) {
+  fkres F;
+  FN(fk)(M, S->q, M->nb, &F);
+  m3 Ree;
+  FN(ee_pose)(M, &F, &SC->eye, &Ree);
+  SC->Rfb = FN(quat_to_m3)(S->pquat);
+  SC->pfb = FN(v3_make)(S->ppos[0], S->ppos[1], S->ppos[2]);
+  for (int b = 0; b < PIH_MAX_BOX; ++b) {
+    int body = (b < M->nbox) ? M->box_body[b] : 0;
+    SC->Rbox[b] = FN(m3_mul)(&F.Rw[body], &M->box_R[b]);
+    SC->cbox[b] = FN(m3_v_add)(&F.Rw[body], M->box_c[b], F.pw[body]);
+  }
+}
+
+/* nearest hit of the ray o + s d (s > smin) with an axis-aligned box of half extents h (box frame) */
+static inline int FN(ray_box)(v3 o, v3 d, v3 h, real smin, real* s_hit, v3* n) {
+  real oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z}, hh[3] = {h.x, h.y, h.z};
+  real s0 = smin, s1 = RC(1e30);
+  int ax0 = -1; real sg0 = RC(0);
+  for (int a = 0; a < 3; ++a) {
+    if (ABS(dd[a]) < RC(1e-12)) { if (ABS(oo[a]) > hh[a]) return 0; continue; }
+    real inv = RC(1) / dd[a];
+    real ta = (-hh[a] - oo[a]) * inv, tb = (hh[a] - oo[a]) * inv;
+    real sgn = RC(-1);
+    if (ta > tb) { real t = ta; ta = tb; tb = t; sgn = RC(1); }
+    if (ta > s0) { s0 = ta; ax0 = a; sg0 = sgn; }
+    if (tb < s1) s1 = tb;
+  }
+  if (s0 > s1 || ax0 < 0) return 0;
+  *s_hit = s0;
+  *n = FN(v3_make)(ax0 == 0 ? sg0 : RC(0), ax0 == 1 ? sg0 : RC(0), ax0 == 2 ? sg0 : RC(0));
+  return 1;
+}
+
+/* nearest hit with a capped cylinder of radius r, half length hl whose axis is the frame's `axis` coordinate
+ * (1 = y for the peg).  (u, v) are the two radial coordinates. */
+static inline int FN(ray_cyl_y)(v3 o, v3 d, real r, real hl, real smin, real* s_hit, v3* n) {
+  int hit = 0; real best = RC(1e30);
+  real a = FMA(d.z, d.z, d.x * d.x), b = FMA(o.z, d.z, o.x * d.x), c = FMA(o.z, o.z, o.x * o.x) - r * r;
+  if (a > RC(1e-12)) {
+    real disc = FMA(b, b, -(a * c));
+    if (disc >= RC(0)) {
+      real s = (-b - SQRT(disc)) / a;
+      real y = FMA(s, d.y, o.y);
+      if (s > smin && ABS(y) <= hl) { best = s; hit = 1; real ir = RC(1) / r; *n = FN(v3_make)(FMA(s, d.x, o.x) * ir, RC(0), FMA(s, d.z, o.z) * ir); }
+    }
+  }
+  if (ABS(d.y) > RC(1e-12)) {
+    real inv = RC(1) / d.y;
+    for (int k = 0; k < 2; ++k) {
+      real yc = k ? -hl : hl;
+      real s = (yc - o.y) * inv;
+      real x = FMA(s, d.x, o.x), z = FMA(s, d.z, o.z);
+      if (s > smin && s < best && FMA(z, z, x * x) <= r * r) { best = s; hit = 1; *n = FN(v3_make)(RC(0), k ? RC(-1) : RC(1), RC(0)); }
+    }
+  }
+  *s_hit = best;
+  return hit;
+}
+
+/* nearest hit with the annular hole: tube r_in <= rho <= r_out, |x| <= hl, axis x, centre at the origin of (o, d) */
+static inline int FN(ray_tube_x)(v3 o, v3 d, real smin, real* s_hit, v3* n) {
+  const real rin = RC(PIH_HOLE_RIN), rout = RC(PIH_HOLE_ROUT), hl = RC(PIH_HOLE_HL);
+  real a = FMA(d.z, d.z, d.y * d.y), b = FMA(o.z, d.z, o.y * d.y), q2 = FMA(o.z, o.z, o.y * o.y);
+  /* slab interval */
+  real sa = smin, sb = RC(1e30); int slab_first = 0; real slab_sign = RC(0);
+  if (ABS(d.x) > RC(1e-12)) {
+    real inv = RC(1) / d.x;
+    real ta = (-hl - o.x) * inv, tb = (hl - o.x) * inv; real sg = RC(-1);
+    if (ta > tb) { real t = ta; ta = tb; tb = t; sg = RC(1); }
+    if (ta > sa) { sa = ta; slab_first = 1; slab_sign = sg; }
+    sb = tb;
+  } else if (ABS(o.x) > hl) return 0;
+  if (!(a > RC(1e-12))) return 0;   /* ray parallel to the axis: looking straight through or at a cap edge-on */
+  real disco = FMA(b, b, -(a * (q2 - rout * rout)));
+  if (disco < RC(0)) return 0;
+  real sq = SQRT(disco), ia = RC(1) / a;
+  real so1 = (-b - sq) * ia, so2 = (-b + sq) * ia;
+  int first_is_slab = slab_first;
+  real s0 = sa, s1 = (sb < so2) ? sb : so2;
+  if (so1 > s0) { s0 = so1; first_is_slab = 0; }
+  if (s0 > s1) return 0;
+  real disci = FMA(b, b, -(a * (q2 - rin * rin)));
+  real si1 = RC(1e30), si2 = RC(-1e30);
+  if (disci > RC(0)) { real sqi = SQRT(disci); si1 = (-b - sqi) * ia; si2 = (-b + sqi) * ia; }
+  if (s0 < si1 || s0 >= si2) {              /* entry point is in the solid */
+    if (first_is_slab && s0 == smin) return 0;
+    *s_hit = s0;
+    if (first_is_slab) *n = FN(v3_make)(slab_sign, RC(0), RC(0));
+    else { real ir = RC(1) / rout; *n = FN(v3_make)(RC(0), FMA(s0, d.y, o.y) * ir, FMA(s0, d.z, o.z) * ir); }
+    return (s0 > smin);
+  }
+  if (si2 < s1 && si2 > smin) {             /* entered through the bore: hit the inner wall from inside */
+    real ir = RC(1) / rin;
+    *s_hit = si2;
+    *n = FN(v3_make)(RC(0), -(FMA(si2, d.y, o.y) * ir), -(FMA(si2, d.z, o.z) * ir));
+    return 1;
+  }
+  return 0;
+}
+
+static void FN(render_pixel)(const model* M, const simcfg* C, const scene* SC, int row, int col, int W, int H, float out[4]) {
+  const real th = RC(PIH_CAM_TAN_HALF_FOV);
+  real ndx = ((real)col + RC(0.5)) / (real)W * RC(2) - RC(1);
+  real ndy = RC(1) - ((real)row + RC(0.5)) / (real)H * RC(2);
+  v3 d = FN(v3_make)(ndx * th, ndy * th, RC(-1));     /* eye-space depth == ray parameter */
+  v3 o = SC->eye;
+  const real smin = RC(PIH_CAM_NEAR);
+  real best = RC(1e30); v3 nb = FN(v3_make)(0, 0, 1); int obj = -1;
+  { real s = o.z - RC(PIH_TABLE_Z); if (s > smin) { best = s; obj = 0; } }
+  { /* free body */
+    v3 ol = FN(m3T_v)(&SC->Rfb, FN(v3_sub)(o, SC->pfb)), dl = FN(m3T_v)(&SC->Rfb, d);
+    real s; v3 n; int h;
+    if (M->fb_shape == 0) h = FN(ray_cyl_y)(ol, dl, M->fb_half.x, M->fb_half.y, smin, &s, &n);
+    else h = FN(ray_box)(ol, dl, M->fb_half, smin, &s, &n);
+    if (h && s < best) { best = s; obj = 1; nb = FN(m3_v)(&SC->Rfb, n); }
+  }
+  if (C->task != PIH_TASK_RANDOM_FLY) {
+    v3 oh = FN(v3_make)(o.x - RC(PIH_HOLE_X), o.y - RC(PIH_HOLE_Y), o.z - RC(PIH_HOLE_Z));
+    real s; v3 n;
+    if (FN(ray_tube_x)(oh, d, smin, &s, &n) && s < best) { best = s; obj = 2; nb = n; }
+  }
+  for (int b = 0; b < M->nbox; ++b) {
+    v3 ol = FN(m3T_v)(&SC->Rbox[b], FN(v3_sub)(o, SC->cbox[b])), dl = FN(m3T_v)(&SC->Rbox[b], d);
+    real s; v3 n;
+    if (FN(ray_box)(ol, dl, M->box_h[b], smin, &s, &n) && s < best) { best = s; obj = 3; nb = FN(m3_v)(&SC->Rbox[b], n); }
+  }
+  const real fn = RC(PIH_CAM_FAR), nn = RC(PIH_CAM_NEAR);
+  real depth = RC(1);
+  real base[3] = {RC(255), RC(255), RC(255)};
+  real shade = RC(1);
+  if (obj >= 0) {
+    depth = FMA(RC(0.5), (fn + nn) / (fn - nn) - (RC(2) * fn * nn) / ((fn - nn) * best), RC(0.5));
+    static const double cols[4][3] = {{153, 128, 102}, {232, 232, 232}, {232, 232, 232}, {204, 204, 204}};
+    base[0] = RC(cols[obj][0]); base[1] = RC(cols[obj][1]); base[2] = RC(cols[obj][2]);
+    const v3 l = FN(v3_make)(RC(0.2672612419124244), RC(0.1781741612749496), RC(0.9449111825230680));
+    real nl = FN(v3_dot)(nb, l);
+    nl = (nl < RC(0)) ? RC(0) : nl;
+    shade = FMA(RC(0.65), nl, RC(0.35));
+  }
+  out[0] = (float)depth;
+  for (int k = 0; k < 3; ++k) {
+    real v = base[k] * shade + RC(0.5);
+    out[1 + k] = (float)(real)(int)v;
+  }
+}
+
 /* returns contact count; outputs written only if the env was stepped (done envs are frozen: base_env.py:61-71) */
 static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real* action, const real off[3], uint32_t gid,
                         real* obs, real* reward, uint8_t* done) {
@@ -1281,6 +1441,7 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
 #undef contact
 #undef contactset
 #undef crow
+#undef scene
 #undef FMA
 #undef SQRT
 #undef RC

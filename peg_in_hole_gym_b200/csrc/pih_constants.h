@@ -100,6 +100,15 @@
 #define PIH_FSM_FINGER_FORCE_LO 20.0
 #define PIH_FSM_FINGER_FORCE_HI 20000.0
 
+/* camera of PegInHole.render (envs/peg_in_hole.py:276-304): eye at the end effector looking along -z, up +y,
+ * FOV 60 deg, aspect 1, near 0.001, far 1000, 300 x 300; output channels (depth, r, g, b) */
+#define PIH_CAM_W 300
+#define PIH_CAM_H 300
+#define PIH_CAM_TAN_HALF_FOV 0.5773502691896257   /* tan(30 deg) */
+#define PIH_CAM_NEAR 0.001
+#define PIH_CAM_FAR 1000.0
+#define PIH_SCENE_WORDS 64      /* per-env scene block handed from the scene pre-pass to the ray caster */
+
 /* RNG stream ids (Philox4x32-10 counter word 2) */
 #define PIH_STREAM_RESET 0
 #define PIH_STREAM_ACTION 1

@@ -7,7 +7,7 @@
 #include <new>
 
 #include "../../include/pih.h"
-#include "pih_step.cuh"
+#include "pih_render.cuh"
 
 namespace pih {
 
@@ -182,6 +182,7 @@ struct pih_handle {
   unsigned char* h_done;
   float *d_action, *d_obs, *d_reward;
   unsigned char* d_done;
+  float* d_scene;  // render pre-pass output [n][PIH_SCENE_WORDS], allocated on first pih_render
 };
 
 static int g_tables_device = -1;
@@ -330,6 +331,7 @@ void pih_destroy(pih_handle* h) {
   if (h->d_obs) cudaFree(h->d_obs);
   if (h->d_reward) cudaFree(h->d_reward);
   if (h->d_done) cudaFree(h->d_done);
+  if (h->d_scene) cudaFree(h->d_scene);
   delete h;
 }
 
@@ -438,6 +440,31 @@ int pih_ee_pose(pih_handle* h, float* pos_dev, float* rot_dev, void* stream) {
   LAUNCH_ARM(k_ee, h, stream, h->P, pos_dev, rot_dev);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_ee launch", ce);
+  return PIH_OK;
+}
+
+int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, void* stream) {
+  if (!h || !rgbd_dev || width <= 0 || height <= 0) return PIH_ERR_INVALID;
+  if (!h->was_reset) return fail(h, PIH_ERR_STATE, "render() before reset()", cudaSuccess);
+  if (!h->d_scene) {
+    cudaError_t ce = cudaMalloc(&h->d_scene, (size_t)h->P.n * PIH_SCENE_WORDS * sizeof(float));
+    if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "scene allocation", ce);
+  }
+  LAUNCH_ARM(k_scene, h, stream, h->P, h->d_scene, (int)width, (int)height);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_scene launch", ce);
+  dim3 grid((unsigned)((width * height + 256 * PIH_RENDER_PPT - 1) / (256 * PIH_RENDER_PPT)), (unsigned)h->P.n);
+  cudaStream_t st = (cudaStream_t)stream;
+  float4* out = reinterpret_cast<float4*>(rgbd_dev);
+#define RLAUNCH(ARMV)                                                                                              \
+  do {                                                                                                             \
+    if (h->P.task == PIH_TASK_RANDOM_FLY) k_render<ARMV, PIH_TASK_RANDOM_FLY><<<grid, 256, 0, st>>>(h->P, h->d_scene, width, height, out); \
+    else k_render<ARMV, PIH_TASK_PEG_IN_HOLE><<<grid, 256, 0, st>>>(h->P, h->d_scene, width, height, out);         \
+  } while (0)
+  if (h->P.arm == PIH_ARM_PANDA) RLAUNCH(PIH_ARM_PANDA); else RLAUNCH(PIH_ARM_UR5);
+#undef RLAUNCH
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_render launch", ce);
   return PIH_OK;
 }
 

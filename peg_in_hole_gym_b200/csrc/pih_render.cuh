@@ -1,0 +1,243 @@
+// pih_render.cuh - batched camera of PegInHole.render (envs/peg_in_hole.py:276-304): a ray caster over the analytic
+// primitives of the scene, one pixel per thread, one float4 (depth, r, g, b) store per pixel.  HBM-write bound
+// (16 B per pixel, 1.44 MB per 300x300 env image).  Same formulas as the oracle's render_pixel.
+#pragma once
+#include "pih_step.cuh"
+
+namespace pih {
+
+#define PIH_RENDER_PPT 8
+
+// Conservative screen-space rectangle (pixel rows/cols) of a bounding sphere (centre c, radius R) seen from eye e by
+// the straight-down camera (camera axes == env axes).  Used only to skip ray tests that cannot hit; never culls a hit.
+PIH_D void screen_rect(v3 e, v3 c, float R, int W, int H, float* out4) {
+  const float ith = 1.0f / (float)PIH_CAM_TAN_HALF_FOV;
+  float dx = c.x - e.x, dy = c.y - e.y, dz = e.z - c.z;
+  R = R * 1.05f + 1e-4f;
+  float r0 = 0.0f, r1 = (float)(H - 1), c0 = 0.0f, c1 = (float)(W - 1);
+  if (dz + R <= 0.0f) { c0 = 1.0f; c1 = 0.0f; }            // entirely behind the camera: empty rectangle
+  else if (dz - R > 1e-3f) {
+    float zn = dz - R, zf = dz + R;
+    float xlo = (dx - R) * ith / ((dx - R >= 0.0f) ? zf : zn), xhi = (dx + R) * ith / ((dx + R >= 0.0f) ? zn : zf);
+    float ylo = (dy - R) * ith / ((dy - R >= 0.0f) ? zf : zn), yhi = (dy + R) * ith / ((dy + R >= 0.0f) ? zn : zf);
+    c0 = fmaxf(c0, floorf((xlo + 1.0f) * 0.5f * (float)W - 0.5f) - 1.0f);
+    c1 = fminf(c1, ceilf((xhi + 1.0f) * 0.5f * (float)W - 0.5f) + 1.0f);
+    r0 = fmaxf(r0, floorf((1.0f - yhi) * 0.5f * (float)H - 0.5f) - 1.0f);
+    r1 = fminf(r1, ceilf((1.0f - ylo) * 0.5f * (float)H - 0.5f) + 1.0f);
+  }
+  out4[0] = r0; out4[1] = r1; out4[2] = c0; out4[3] = c1;
+}
+
+// scene block per env: eye(3) Rfb(9) pfb(3) Rbox0(9) cbox0(3) Rbox1(9) cbox1(3) | 39: screen rects (r0,r1,c0,c1) of the
+// free body, the hole and the two finger boxes
+template <int ARM> __global__ void __launch_bounds__(128) k_scene(SimParams P, float* __restrict__ scene, int W, int H) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.n) return;
+  constexpr int nb = ArmDims<ARM>::NB;
+  const ArmTables& T = c_arm[ARM];
+  EnvState S;
+  load_state(P, e, S);
+  FK<ARM> F;
+  fk<ARM, nb>(S.q, F);
+  v3 eye; m3 Ree;
+  ee_pose<ARM>(F, eye, Ree);
+  float* o = scene + (size_t)PIH_SCENE_WORDS * e;
+  o[0] = eye.x; o[1] = eye.y; o[2] = eye.z;
+  m3 Rfb = quat_to_m3(S.pquat);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) o[3 + i] = Rfb.m[i / 3][i % 3];
+  o[12] = S.ppos[0]; o[13] = S.ppos[1]; o[14] = S.ppos[2];
+  sfor<0, PIH_MAX_BOX>([&](auto b_) {
+    constexpr int b = decltype(b_)::value;
+    constexpr int body = (b < ArmGeom<ARM>::NBOX) ? box_body_of<ARM>(b) : 0;
+    m3 Rb = mmul(F.Rw[body], ldm(T.box_R[b]));
+    v3 cb = mv_add(F.Rw[body], ld3(T.box_c[b]), F.pw[body]);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[15 + 12 * b + i] = Rb.m[i / 3][i % 3];
+    o[24 + 12 * b] = cb.x; o[25 + 12 * b] = cb.y; o[26 + 12 * b] = cb.z;
+    screen_rect(eye, cb, T.box_h[b][0] + T.box_h[b][1] + T.box_h[b][2], W, H, o + 47 + 4 * b);
+  });
+  screen_rect(eye, mk(S.ppos[0], S.ppos[1], S.ppos[2]), P.fb_half[0] + P.fb_half[1] + P.fb_half[2], W, H, o + 39);
+  screen_rect(eye, mk((float)PIH_HOLE_X, (float)PIH_HOLE_Y, (float)PIH_HOLE_Z), (float)(PIH_HOLE_ROUT + PIH_HOLE_HL), W, H, o + 43);
+}
+
+PIH_D bool ray_box(v3 o, v3 d, v3 h, float smin, float& s_hit, v3& n) {
+  float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z}, hh[3] = {h.x, h.y, h.z};
+  float s0 = smin, s1 = 1e30f;
+  int ax0 = -1;
+  float sg0 = 0.0f;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (fabsf(dd[a]) < 1e-12f) {
+      if (fabsf(oo[a]) > hh[a]) return false;
+      continue;
+    }
+    float inv = 1.0f / dd[a];
+    float ta = (-hh[a] - oo[a]) * inv, tb = (hh[a] - oo[a]) * inv;
+    float sgn = -1.0f;
+    if (ta > tb) { float t = ta; ta = tb; tb = t; sgn = 1.0f; }
+    if (ta > s0) { s0 = ta; ax0 = a; sg0 = sgn; }
+    if (tb < s1) s1 = tb;
+  }
+  if (s0 > s1 || ax0 < 0) return false;
+  s_hit = s0;
+  n = mk(ax0 == 0 ? sg0 : 0.0f, ax0 == 1 ? sg0 : 0.0f, ax0 == 2 ? sg0 : 0.0f);
+  return true;
+}
+
+PIH_D bool ray_cyl_y(v3 o, v3 d, float r, float hl, float smin, float& s_hit, v3& n) {
+  bool hit = false;
+  float best = 1e30f;
+  float a = fmaf(d.z, d.z, d.x * d.x), b = fmaf(o.z, d.z, o.x * d.x), c = fmaf(o.z, o.z, o.x * o.x) - r * r;
+  if (a > 1e-12f) {
+    float disc = fmaf(b, b, -(a * c));
+    if (disc >= 0.0f) {
+      float s = (-b - sqrtf(disc)) / a;
+      float y = fmaf(s, d.y, o.y);
+      if (s > smin && fabsf(y) <= hl) { best = s; hit = true; float ir = 1.0f / r; n = mk(fmaf(s, d.x, o.x) * ir, 0.0f, fmaf(s, d.z, o.z) * ir); }
+    }
+  }
+  if (fabsf(d.y) > 1e-12f) {
+    float inv = 1.0f / d.y;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float yc = k ? -hl : hl;
+      float s = (yc - o.y) * inv;
+      float x = fmaf(s, d.x, o.x), z = fmaf(s, d.z, o.z);
+      if (s > smin && s < best && fmaf(z, z, x * x) <= r * r) { best = s; hit = true; n = mk(0.0f, k ? -1.0f : 1.0f, 0.0f); }
+    }
+  }
+  s_hit = best;
+  return hit;
+}
+
+PIH_D bool ray_tube_x(v3 o, v3 d, float smin, float& s_hit, v3& n) {
+  const float rin = (float)PIH_HOLE_RIN, rout = (float)PIH_HOLE_ROUT, hl = (float)PIH_HOLE_HL;
+  float a = fmaf(d.z, d.z, d.y * d.y), b = fmaf(o.z, d.z, o.y * d.y), q2 = fmaf(o.z, o.z, o.y * o.y);
+  float sa = smin, sb = 1e30f;
+  bool slab_first = false;
+  float slab_sign = 0.0f;
+  if (fabsf(d.x) > 1e-12f) {
+    float inv = 1.0f / d.x;
+    float ta = (-hl - o.x) * inv, tb = (hl - o.x) * inv, sg = -1.0f;
+    if (ta > tb) { float t = ta; ta = tb; tb = t; sg = 1.0f; }
+    if (ta > sa) { sa = ta; slab_first = true; slab_sign = sg; }
+    sb = tb;
+  } else if (fabsf(o.x) > hl) return false;
+  if (!(a > 1e-12f)) return false;
+  float disco = fmaf(b, b, -(a * (q2 - rout * rout)));
+  if (disco < 0.0f) return false;
+  float sq = sqrtf(disco), ia = 1.0f / a;
+  float so1 = (-b - sq) * ia, so2 = (-b + sq) * ia;
+  bool first_is_slab = slab_first;
+  float s0 = sa, s1 = (sb < so2) ? sb : so2;
+  if (so1 > s0) { s0 = so1; first_is_slab = false; }
+  if (s0 > s1) return false;
+  float disci = fmaf(b, b, -(a * (q2 - rin * rin)));
+  float si1 = 1e30f, si2 = -1e30f;
+  if (disci > 0.0f) { float sqi = sqrtf(disci); si1 = (-b - sqi) * ia; si2 = (-b + sqi) * ia; }
+  if (s0 < si1 || s0 >= si2) {
+    if (first_is_slab && s0 == smin) return false;
+    s_hit = s0;
+    if (first_is_slab) n = mk(slab_sign, 0.0f, 0.0f);
+    else { float ir = 1.0f / rout; n = mk(0.0f, fmaf(s0, d.y, o.y) * ir, fmaf(s0, d.z, o.z) * ir); }
+    return s0 > smin;
+  }
+  if (si2 < s1 && si2 > smin) {
+    float ir = 1.0f / rin;
+    s_hit = si2;
+    n = mk(0.0f, -(fmaf(si2, d.y, o.y) * ir), -(fmaf(si2, d.z, o.z) * ir));
+    return true;
+  }
+  return false;
+}
+
+// conservative sphere cull: can the ray o + s d come within `rad` of centre c?  (never rejects a true hit)
+PIH_D bool near_sphere(v3 o, v3 d, v3 c, float rad) {
+  v3 oc = vsub(c, o);
+  float dd = vdot(d, d), t = vdot(oc, d);
+  float perp2 = vdot(oc, oc) * dd - t * t;         // |oc x d|^2
+  return perp2 <= rad * rad * dd * 1.1f + 1e-9f;
+}
+
+template <int ARM, int TASK> __global__ void __launch_bounds__(256, 4) k_render(SimParams P, const float* __restrict__ scene, int W, int H,
+                                                                          float4* __restrict__ out) {
+  __shared__ float sc[PIH_SCENE_WORDS];
+  const int e = blockIdx.y;
+  if (threadIdx.x < PIH_SCENE_WORDS) sc[threadIdx.x] = scene[(size_t)PIH_SCENE_WORDS * e + threadIdx.x];
+  __syncthreads();
+  // PIH_RENDER_PPT pixels per thread, strided by the block size so that every warp store is 512 contiguous bytes
+  const ArmTables& T = c_arm[ARM];
+#pragma unroll 1
+  for (int it = 0; it < PIH_RENDER_PPT; ++it) {
+  const int pix = (blockIdx.x * PIH_RENDER_PPT + it) * blockDim.x + threadIdx.x;
+  if (pix >= W * H) return;
+  const int row = pix / W, col = pix - row * W;
+  const float frow = (float)row, fcol = (float)col;
+#define IN_RECT(base) (frow >= sc[(base)] && frow <= sc[(base) + 1] && fcol >= sc[(base) + 2] && fcol <= sc[(base) + 3])
+  const float th = (float)PIH_CAM_TAN_HALF_FOV;
+  float ndx = ((float)col + 0.5f) / (float)W * 2.0f - 1.0f;
+  float ndy = 1.0f - ((float)row + 0.5f) / (float)H * 2.0f;
+  v3 d = mk(ndx * th, ndy * th, -1.0f);
+  v3 o = mk(sc[0], sc[1], sc[2]);
+  const float smin = (float)PIH_CAM_NEAR;
+  float best = 1e30f;
+  v3 nb = mk(0.0f, 0.0f, 1.0f);
+  int obj = -1;
+  { float s = o.z - (float)PIH_TABLE_Z; if (s > smin) { best = s; obj = 0; } }
+  {
+    m3 Rfb;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rfb.m[i / 3][i % 3] = sc[3 + i];
+    v3 pfb = mk(sc[12], sc[13], sc[14]);
+    if (IN_RECT(39)) {
+      v3 ol = mTv(Rfb, vsub(o, pfb)), dl = mTv(Rfb, d);
+      float s; v3 n; bool h;
+      if (TASK != PIH_TASK_RANDOM_FLY) h = ray_cyl_y(ol, dl, P.fb_half[0], P.fb_half[1], smin, s, n);
+      else h = ray_box(ol, dl, mk(P.fb_half[0], P.fb_half[1], P.fb_half[2]), smin, s, n);
+      if (h && s < best) { best = s; obj = 1; nb = mv(Rfb, n); }
+    }
+  }
+  if (TASK != PIH_TASK_RANDOM_FLY) {
+    if (IN_RECT(43)) {
+      v3 oh = mk(o.x - (float)PIH_HOLE_X, o.y - (float)PIH_HOLE_Y, o.z - (float)PIH_HOLE_Z);
+      float s; v3 n;
+      if (ray_tube_x(oh, d, smin, s, n) && s < best) { best = s; obj = 2; nb = n; }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < ArmGeom<ARM>::NBOX; ++b) {
+    m3 Rb;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rb.m[i / 3][i % 3] = sc[15 + 12 * b + i];
+    v3 cb = mk(sc[24 + 12 * b], sc[25 + 12 * b], sc[26 + 12 * b]);
+    v3 hb = ld3(T.box_h[b]);
+    if (IN_RECT(47 + 4 * b)) {
+      v3 ol = mTv(Rb, vsub(o, cb)), dl = mTv(Rb, d);
+      float s; v3 n;
+      if (ray_box(ol, dl, hb, smin, s, n) && s < best) { best = s; obj = 3; nb = mv(Rb, n); }
+    }
+  }
+  const float fn = (float)PIH_CAM_FAR, nn = (float)PIH_CAM_NEAR;
+  float depth = 1.0f, r = 255.0f, g = 255.0f, bl = 255.0f, shade = 1.0f;
+  if (obj >= 0) {
+    depth = fmaf(0.5f, (fn + nn) / (fn - nn) - (2.0f * fn * nn) / ((fn - nn) * best), 0.5f);
+    r = (obj == 0) ? 153.0f : (obj == 3) ? 204.0f : 232.0f;
+    g = (obj == 0) ? 128.0f : (obj == 3) ? 204.0f : 232.0f;
+    bl = (obj == 0) ? 102.0f : (obj == 3) ? 204.0f : 232.0f;
+    const v3 l = mk((float)0.2672612419124244, (float)0.1781741612749496, (float)0.9449111825230680);
+    float nl = vdot(nb, l);
+    nl = (nl < 0.0f) ? 0.0f : nl;
+    shade = fmaf(0.65f, nl, 0.35f);
+  }
+  float4 px;
+  px.x = depth;
+  px.y = (float)(int)(r * shade + 0.5f);
+  px.z = (float)(int)(g * shade + 0.5f);
+  px.w = (float)(int)(bl * shade + 0.5f);
+  out[(size_t)e * W * H + pix] = px;
+  }
+#undef IN_RECT
+}
+
+}  // namespace pih

@@ -105,8 +105,9 @@ class BaseEnv(gym.Env):
             test_mode('r', self.reset)
         return self._pack(obs, reward, done)
 
-    def render(self, mode='rgb_array'):
-        return self.plugin.render(mode)
+    def render(self, mode='rgb_array', width=300, height=300):
+        img = self.plugin.render(mode, width, height)
+        return img.view(*self._shape(), height, width, 4)
 
     def reset(self, hard_reset=False):
         self.plugin.reset(hard_reset)

@@ -40,5 +40,5 @@ class BaseEnvMp(BaseEnv):
     def _shape(self):
         return (self.mp_num, self.sub_num)
 
-    def render(self, mode='rgb_array'):
-        return None  # the reference only posts RENDER to the workers and returns nothing (base_env_mp.py:66-68)
+    # render(mode): the reference only posts RENDER to the workers and discards the images (base_env_mp.py:66-68); here
+    # the inherited BaseEnv.render returns them as a [mp, sub, H, W, 4] tensor.

@@ -61,8 +61,9 @@ class MetaEnv(object):
         self._reset_internals()
         self.done = False
 
-    def render(self, mode="rgb_array"):
-        raise NotImplementedError("camera rendering is SURVEY.md section 8f rank 3 (next), not on the step path")
+    def render(self, mode="rgb_array", width=300, height=300):
+        """peg_in_hole.py:276-304: end-effector camera, [N, 300, 300, 4] = (depth, r, g, b)."""
+        return self.p.render(width, height)
 
     def test_mode(self, test_key, func):
         return None

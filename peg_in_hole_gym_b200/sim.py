@@ -103,6 +103,13 @@ class BatchedSim:
         N.check(self._L.pih_ee_pose(self._h, pos.data_ptr(), rot.data_ptr(), self._stream()), self._h, "pih_ee_pose")
         return pos, rot.view(self.n, 3, 3)
 
+    def render(self, width=300, height=300, out=None):
+        """PegInHole.render (peg_in_hole.py:276-304) for all envs: [N, H, W, 4] = (depth, r, g, b)."""
+        if out is None:
+            out = torch.empty(self.n, height, width, 4, dtype=torch.float32, device=self.device)
+        N.check(self._L.pih_render(self._h, int(width), int(height), out.data_ptr(), self._stream()), self._h, "pih_render")
+        return out
+
     # -- state views (SoA words -> [N, k]); copies, for tests / checkpointing
     def words(self, first, count=1):
         flat = self.state.permute(1, 0, 2).reshape(self.n, -1)

@@ -74,6 +74,7 @@ def lib():
         L.pih_oracle_atan2_q1.argtypes = [C.c_float, C.c_float]
         L.pih_oracle_rng4.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.pih_oracle_philox.argtypes = [C.c_void_p] * 3
+        L.pih_oracle_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -124,6 +125,12 @@ class Oracle:
         if rc != 0:
             raise RuntimeError(f"oracle rollout rc={rc}")
         return self.obs.copy(), self.reward.copy(), self.done.copy(), cnt
+
+    def render(self, width=300, height=300, lo=0, hi=None):
+        hi = self.n if hi is None else hi
+        img = np.zeros((hi - lo, height, width, 4), np.float32)
+        lib().pih_oracle_render(self.h, width, height, lo, hi, _p(img))
+        return img
 
     def get_state(self):
         w = np.zeros((STATE_WORDS // 4, self.n, 4), np.float32)

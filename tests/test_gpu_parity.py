@@ -319,3 +319,26 @@ def test_scripted_grasp_fsm_bit_exact_and_through_gym_surface():
     obs, reward, done, info = env.step(env.action_space.sample_array())      # one step() = one scripted episode
     assert bool(done.all()) and np.array_equal(reward.cpu().numpy().ravel(), orc.reward)
     env.close()
+
+
+def test_camera_render_matches_oracle_and_full_size():
+    """PegInHole.render as a batched ray caster; CUDA image == oracle image, then 300x300."""
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    n = 6
+    sim = BatchedSim(n, task="peg-in-hole-scripted", offset=(2.0, 3.0, 0.0), seed=3, device=0)
+    orc = ol.Oracle(ol.make_config(n, task=2, offset=(2.0, 3.0, 0.0), seed=3))
+    sim.reset(); orc.reset()
+    for steps in (560, 600, 900):                            # hovering over the peg / grasping / at the hole
+        sim.rollout(steps); orc.rollout(steps)
+        g = sim.render(80, 64).cpu().numpy()
+        c = orc.render(80, 64)
+        assert np.array_equal(g[..., 1:], c[..., 1:]), "rgb differs"
+        assert np.array_equal(g[..., 0], c[..., 0]), "depth differs"
+    img = sim.render()                                       # reference resolution (peg_in_hole.py:24-26)
+    assert tuple(img.shape) == (n, 300, 300, 4)
+    assert float(img[..., 0].min()) > 0.0 and float(img[..., 0].max()) <= 1.0
+    import peg_in_hole_gym_b200 as gym
+    env = gym.make('peg-in-hole-mp-v0', client=gym.DIRECT, task='peg-in-hole', mp_num=2, sub_num=2, offset=[2., 3., 0.], shard=False)
+    env.reset()
+    assert tuple(env.render('rgb_array').shape) == (2, 2, 300, 300, 4)
+    env.close()

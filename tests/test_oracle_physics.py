@@ -198,3 +198,22 @@ def test_scripted_grasp_fsm_runs_the_reference_schedule():
     assert np.isfinite(w).all() and seen_hole
     assert r.mean() >= 0.25                           # some pegs end within 5 cm of the hole (peg_in_hole.py:114-117)
     assert np.allclose(obs[:, 2:5] - np.array([[2.0 * (i // 4), 3.0 * (i % 4), 0.0] for i in range(n)]), [0.2, -0.6, 0.4], atol=0.02)
+
+
+def test_camera_render_sees_table_and_peg():
+    """PegInHole.render (peg_in_hole.py:276-304): camera at the end effector looking down; depth is the OpenGL
+    depth-buffer encoding for near 0.001 / far 1000; the peg below the gripper shows up as a bright bar."""
+    o = ol.Oracle(ol.make_config(2, task=2, offset=(2.0, 0.0, 0.0), seed=3))
+    o.reset()
+    a = np.zeros((2, 4), np.float32)
+    for _ in range(560):
+        o.step(a)                                            # FSM state 2: gripper hovering over the peg
+    img = o.render(60, 60)
+    assert img.shape == (2, 60, 60, 4)
+    depth, rgb = img[..., 0], img[..., 1:]
+    assert 0.99 < depth.min() <= depth.max() <= 1.0
+    ee_z = o.obs[0, 4]
+    z_table = 0.001 * 1000.0 / (1000.0 - depth[0, 0, 0] * (1000.0 - 0.001))     # invert the depth encoding
+    assert abs(z_table - (ee_z + 0.05)) < 2e-3               # corner pixel sees the table at z = -0.05
+    assert (rgb[0, 30, 30] > rgb[0, 0, 0]).all()             # peg (white) in the image centre, table (brown) at the corner
+    assert np.array_equal(rgb, np.round(rgb)) and rgb.min() >= 0 and rgb.max() <= 255
