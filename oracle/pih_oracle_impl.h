@@ -1306,35 +1306,45 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
   real dva[NBM];
   for (int j = 0; j < nb; ++j) dva[j] = RC(0);
   v3 dvl = FN(v3_make)(0, 0, 0), dvw = dvl;
-  /* early exit: PyBullet's solverResidualThreshold (default 1e-7) on the largest squared velocity change
-   * (deltaImpulse / jacDiagABInv)^2 of any row in the iteration [3P] */
+  /* Early exit: PyBullet's solverResidualThreshold (default 1e-7) on the largest squared velocity change
+   * (deltaImpulse / jacDiagABInv)^2 of any row in the iteration [3P].  Like Bullet's simulation islands, bodies that
+   * share no constraint are solved independently: the arm island (motors, limits, arm-table contacts) and the
+   * free-body island (free body vs static geometry) each stop on their own residual; a finger<->free-body contact
+   * merges them into one island. */
+  int coupled = 0;
+  for (int k = 0; k < CS.n; ++k) if (rows[k].has_fb && rows[k].arm_body >= 0) coupled = 1;
+  int arm_on = 1, fb_on = 1;
   for (int it = 0; it < C->solver_iters; ++it) {
-    real res2 = RC(0);
-#define PIH_RES(dl_, diag_) do { real rv_ = (dl_) * (diag_); rv_ = rv_ * rv_; if (rv_ > res2) res2 = rv_; } while (0)
-    for (int j = 0; j < nb; ++j) {
-      real dl = FMA(-dva[j], m_dinv[j], m_b[j]);
-      real s = m_lam[j] + dl;
-      s = (s > m_max[j]) ? m_max[j] : ((s < -m_max[j]) ? -m_max[j] : s);
-      dl = s - m_lam[j];
-      m_lam[j] = s;
-      PIH_RES(dl, Minv[j][j]);
-      for (int i = 0; i < nb; ++i) dva[i] = FMA(Minv[i][j], dl, dva[i]);
-    }
-    for (int j = 0; j < nb; ++j)
-      for (int side = 0; side < 2; ++side) {
-        if (!l_on[side][j]) continue;
-        real sg = side ? RC(-1) : RC(1);
-        real dl = FMA(-(sg * dva[j]), m_dinv[j], l_b[side][j]);
-        real s = l_lam[side][j] + dl;
-        s = (s < RC(0)) ? RC(0) : s;
-        dl = (s - l_lam[side][j]) * sg;
-        l_lam[side][j] = s;
-        PIH_RES(dl, Minv[j][j]);
+    real res_a = RC(0), res_f = RC(0);
+#define PIH_RES(acc_, dl_, diag_) do { real rv_ = (dl_) * (diag_); rv_ = rv_ * rv_; if (rv_ > acc_) acc_ = rv_; } while (0)
+    if (arm_on) {
+      for (int j = 0; j < nb; ++j) {
+        real dl = FMA(-dva[j], m_dinv[j], m_b[j]);
+        real s = m_lam[j] + dl;
+        s = (s > m_max[j]) ? m_max[j] : ((s < -m_max[j]) ? -m_max[j] : s);
+        dl = s - m_lam[j];
+        m_lam[j] = s;
+        PIH_RES(res_a, dl, Minv[j][j]);
         for (int i = 0; i < nb; ++i) dva[i] = FMA(Minv[i][j], dl, dva[i]);
       }
+      for (int j = 0; j < nb; ++j)
+        for (int side = 0; side < 2; ++side) {
+          if (!l_on[side][j]) continue;
+          real sg = side ? RC(-1) : RC(1);
+          real dl = FMA(-(sg * dva[j]), m_dinv[j], l_b[side][j]);
+          real s = l_lam[side][j] + dl;
+          s = (s < RC(0)) ? RC(0) : s;
+          dl = (s - l_lam[side][j]) * sg;
+          l_lam[side][j] = s;
+          PIH_RES(res_a, dl, Minv[j][j]);
+          for (int i = 0; i < nb; ++i) dva[i] = FMA(Minv[i][j], dl, dva[i]);
+        }
+    }
     for (int pass = 0; pass < 2; ++pass)
       for (int k = 0; k < CS.n; ++k) {
         crow* r = &rows[k];
+        const int is_fb = r->has_fb && r->arm_body < 0;
+        if (!coupled && !(is_fb ? fb_on : arm_on)) continue;
         for (int d = (pass ? 1 : 0); d < (pass ? 3 : 1); ++d) {
           real rel = RC(0);
           if (r->has_fb) rel = FN(v3_dot)(r->dir[d], dvl) + FN(v3_dot)(r->jang[d], dvw);
@@ -1352,14 +1362,20 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
           }
           dl = s - r->lam[d];
           r->lam[d] = s;
-          PIH_RES(dl, r->diag[d]);
+          if (is_fb) PIH_RES(res_f, dl, r->diag[d]); else PIH_RES(res_a, dl, r->diag[d]);
           if (r->has_fb) { dvl = FN(v3_axpy)(dl * im, r->dir[d], dvl); dvw = FN(v3_axpy)(dl, r->mang[d], dvw); }
           if (r->arm_body >= 0) for (int j = 0; j < nb; ++j) dva[j] = FMA(r->ma[d][j], dl, dva[j]);
         }
       }
 #undef PIH_RES
     pih_dbg_pgs_iters += 1;
-    if (res2 <= C->solver_residual) break;
+    if (coupled) {
+      if (((res_a > res_f) ? res_a : res_f) <= C->solver_residual) break;
+    } else {
+      if (res_a <= C->solver_residual) arm_on = 0;
+      if (res_f <= C->solver_residual) fb_on = 0;
+      if (!arm_on && !fb_on) break;
+    }
   }
   pih_dbg_pgs_steps += 1;
   /* ---- integrate (semi-implicit Euler) ---- */

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpih_b200.so")
+LIB_PATH = os.environ.get("PIH_LIB", os.path.join(_HERE, "csrc", "libpih_b200.so"))  # PIH_LIB: perf experiments only
 
 PIH_OK, PIH_ERR_INVALID, PIH_ERR_CUDA, PIH_ERR_STATE = 0, -1, -2, -3
 TASK_IDS = {"peg-in-hole": 0, "random-fly": 1, "peg-in-hole-scripted": 2}

@@ -11,6 +11,10 @@
 
 namespace pih {
 
+// register budget of the step kernels: PIH_MIN_BLOCKS CTAs of 128 threads per SM (1 -> 255 regs, 4 -> 128 regs)
+#ifndef PIH_MIN_BLOCKS
+#define PIH_MIN_BLOCKS 1
+#endif
 
 // ------------------------------------------------------------------------------------------------ kernels
 // thread-per-env; grid = ceil(n / blockDim).  State is read once and written once per launch as float4 SoA.
@@ -32,7 +36,7 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128) k_reset(SimP
   }
 }
 
-template <int ARM, int TASK> __global__ void __launch_bounds__(128) k_step(SimParams P, const float* __restrict__ action, float* __restrict__ obs,
+template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOCKS) k_step(SimParams P, const float* __restrict__ action, float* __restrict__ obs,
                                                                 float* __restrict__ reward, unsigned char* __restrict__ done) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.n) return;
@@ -59,7 +63,7 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128) k_step(SimPa
   if (done) done[e] = d;
 }
 
-template <int ARM, int TASK> __global__ void __launch_bounds__(128) k_rollout(SimParams P, int steps, float* __restrict__ obs, float* __restrict__ reward,
+template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOCKS) k_rollout(SimParams P, int steps, float* __restrict__ obs, float* __restrict__ reward,
                                                                    unsigned char* __restrict__ done, unsigned long long* __restrict__ counters) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.n) return;

@@ -482,13 +482,14 @@ template <int ARM, int TASK> __device__ __noinline__ bool step_env(const SimPara
   collide<ARM, TASK>(P, S, F, Rfb, CS);
   CRow<ARM> rows[PIH_MAXC];
   int pairmask = 0;
-  bool arm_contacts = false;
+  bool arm_contacts = false, coupled = false;
   v3 pfb = mk(S.ppos[0], S.ppos[1], S.ppos[2]);
   for (int k = 0; k < CS.n; ++k) {
     const Contact& c = CS.c[k];
     CRow<ARM>& r = rows[k];
     pairmask |= c.pair;
     arm_contacts = arm_contacts || (c.arm_body >= 0);
+    coupled = coupled || (c.has_fb && c.arm_body >= 0);
     r.has_fb = c.has_fb; r.arm_body = c.arm_body; r.mu = c.mu;
     r.dir[0] = c.n;
     plane_space(c.n, r.dir[1], r.dir[2]);
@@ -541,79 +542,87 @@ template <int ARM, int TASK> __device__ __noinline__ bool step_env(const SimPara
     }
   }
   // ---- projected Gauss-Seidel: motors, limits, contact normals, contact friction.  Early exit on PyBullet's
-  //      solverResidualThreshold: largest squared velocity change (deltaImpulse / jacDiagABInv)^2 of the iteration.
+  //      solverResidualThreshold: largest squared velocity change (deltaImpulse / jacDiagABInv)^2 of the iteration,
+  //      evaluated per simulation island (arm island / free-body island; merged by a finger<->free-body contact).
   float dva[nb];
 #pragma unroll
   for (int j = 0; j < nb; ++j) dva[j] = 0.0f;
   v3 dvl = mk(0.0f, 0.0f, 0.0f), dvw = dvl;
   const int ncon = CS.n;
+  bool arm_on = true, fb_on = true;
   for (int it = 0; it < P.solver_iters; ++it) {
-    float res2 = 0.0f;
-#pragma unroll
-    for (int j = 0; j < nb; ++j) {
-      float dl = fmaf(-dva[j], m_dinv[j], m_b[j]);
-      float s = m_lam[j] + dl;
-      s = fminf(fmaxf(s, -m_max[j]), m_max[j]);
-      dl = s - m_lam[j];
-      m_lam[j] = s;
-      float rv = dl * Minv[j][j];
-      res2 = fmaxf(res2, rv * rv);
-#pragma unroll
-      for (int i = 0; i < nb; ++i) dva[i] = fmaf(Minv[i][j], dl, dva[i]);
-    }
-    if (l_on) {  // uniform-ish skip: most steps only the finger limit rows exist
+    float res_a = 0.0f, res_f = 0.0f;
+    if (arm_on) {
 #pragma unroll
       for (int j = 0; j < nb; ++j) {
+        float dl = fmaf(-dva[j], m_dinv[j], m_b[j]);
+        float s = m_lam[j] + dl;
+        s = fminf(fmaxf(s, -m_max[j]), m_max[j]);
+        dl = s - m_lam[j];
+        m_lam[j] = s;
+        float rv = dl * Minv[j][j];
+        res_a = fmaxf(res_a, rv * rv);
 #pragma unroll
-        for (int side = 0; side < 2; ++side) {
-          if (!((l_on >> (2 * j + side)) & 1u)) continue;
-          float sg = side ? -1.0f : 1.0f;
-          float dl = fmaf(-(sg * dva[j]), m_dinv[j], l_b[side][j]);
-          float s = l_lam[side][j] + dl;
-          s = fmaxf(s, 0.0f);
-          dl = (s - l_lam[side][j]) * sg;
-          l_lam[side][j] = s;
-          float rv = dl * Minv[j][j];
-          res2 = fmaxf(res2, rv * rv);
+        for (int i = 0; i < nb; ++i) dva[i] = fmaf(Minv[i][j], dl, dva[i]);
+      }
+      if (l_on) {  // uniform-ish skip: most steps only the finger limit rows exist
 #pragma unroll
-          for (int i = 0; i < nb; ++i) dva[i] = fmaf(Minv[i][j], dl, dva[i]);
+        for (int j = 0; j < nb; ++j) {
+#pragma unroll
+          for (int side = 0; side < 2; ++side) {
+            if (!((l_on >> (2 * j + side)) & 1u)) continue;
+            float sg = side ? -1.0f : 1.0f;
+            float dl = fmaf(-(sg * dva[j]), m_dinv[j], l_b[side][j]);
+            float s = l_lam[side][j] + dl;
+            s = fmaxf(s, 0.0f);
+            dl = (s - l_lam[side][j]) * sg;
+            l_lam[side][j] = s;
+            float rv = dl * Minv[j][j];
+            res_a = fmaxf(res_a, rv * rv);
+#pragma unroll
+            for (int i = 0; i < nb; ++i) dva[i] = fmaf(Minv[i][j], dl, dva[i]);
+          }
         }
       }
     }
     if (!arm_contacts) {
       // common case: every contact is free body vs static geometry -> no per-row type branches, no arm coupling
-      for (int k = 0; k < ncon; ++k) {
-        CRow<ARM>& r = rows[k];
-        float rel = vdot(r.dir[0], dvl) + vdot(r.jang[0], dvw);
-        float dl = fmaf(-rel, r.dinv[0], r.b[0]);
-        float s = fmaxf(r.lam[0] + dl, 0.0f);
-        dl = s - r.lam[0];
-        r.lam[0] = s;
-        float rv = dl * r.diag[0];
-        res2 = fmaxf(res2, rv * rv);
-        dvl = vaxpy(dl * im, r.dir[0], dvl);
-        dvw = vaxpy(dl, r.mang[0], dvw);
-      }
-      for (int k = 0; k < ncon; ++k) {
-        CRow<ARM>& r = rows[k];
-        const float lim = r.mu * r.lam[0];
+      if (fb_on) {
+        for (int k = 0; k < ncon; ++k) {
+          CRow<ARM>& r = rows[k];
+          float rel = vdot(r.dir[0], dvl) + vdot(r.jang[0], dvw);
+          float dl = fmaf(-rel, r.dinv[0], r.b[0]);
+          float s = fmaxf(r.lam[0] + dl, 0.0f);
+          dl = s - r.lam[0];
+          r.lam[0] = s;
+          float rv = dl * r.diag[0];
+          res_f = fmaxf(res_f, rv * rv);
+          dvl = vaxpy(dl * im, r.dir[0], dvl);
+          dvw = vaxpy(dl, r.mang[0], dvw);
+        }
+        for (int k = 0; k < ncon; ++k) {
+          CRow<ARM>& r = rows[k];
+          const float lim = r.mu * r.lam[0];
 #pragma unroll
-        for (int d = 1; d < 3; ++d) {
-          float rel = vdot(r.dir[d], dvl) + vdot(r.jang[d], dvw);
-          float dl = fmaf(-rel, r.dinv[d], r.b[d]);
-          float s = fminf(fmaxf(r.lam[d] + dl, -lim), lim);
-          dl = s - r.lam[d];
-          r.lam[d] = s;
-          float rv = dl * r.diag[d];
-          res2 = fmaxf(res2, rv * rv);
-          dvl = vaxpy(dl * im, r.dir[d], dvl);
-          dvw = vaxpy(dl, r.mang[d], dvw);
+          for (int d = 1; d < 3; ++d) {
+            float rel = vdot(r.dir[d], dvl) + vdot(r.jang[d], dvw);
+            float dl = fmaf(-rel, r.dinv[d], r.b[d]);
+            float s = fminf(fmaxf(r.lam[d] + dl, -lim), lim);
+            dl = s - r.lam[d];
+            r.lam[d] = s;
+            float rv = dl * r.diag[d];
+            res_f = fmaxf(res_f, rv * rv);
+            dvl = vaxpy(dl * im, r.dir[d], dvl);
+            dvw = vaxpy(dl, r.mang[d], dvw);
+          }
         }
       }
     } else {
       for (int pass = 0; pass < 2; ++pass)
         for (int k = 0; k < ncon; ++k) {
           CRow<ARM>& r = rows[k];
+          const bool is_fb = r.has_fb && r.arm_body < 0;
+          if (!coupled && !(is_fb ? fb_on : arm_on)) continue;
           for (int d = (pass ? 1 : 0); d < (pass ? 3 : 1); ++d) {
             float rel = 0.0f;
             if (r.has_fb) rel = vdot(r.dir[d], dvl) + vdot(r.jang[d], dvw);
@@ -633,7 +642,7 @@ template <int ARM, int TASK> __device__ __noinline__ bool step_env(const SimPara
             dl = s - r.lam[d];
             r.lam[d] = s;
             float rv = dl * r.diag[d];
-            res2 = fmaxf(res2, rv * rv);
+            if (is_fb) res_f = fmaxf(res_f, rv * rv); else res_a = fmaxf(res_a, rv * rv);
             if (r.has_fb) { dvl = vaxpy(dl * im, r.dir[d], dvl); dvw = vaxpy(dl, r.mang[d], dvw); }
             if (r.arm_body >= 0) {
 #pragma unroll
@@ -642,7 +651,13 @@ template <int ARM, int TASK> __device__ __noinline__ bool step_env(const SimPara
           }
         }
     }
-    if (res2 <= P.solver_residual) break;
+    if (coupled) {
+      if (fmaxf(res_a, res_f) <= P.solver_residual) break;
+    } else {
+      if (res_a <= P.solver_residual) arm_on = false;
+      if (res_f <= P.solver_residual) fb_on = false;
+      if (!arm_on && !fb_on) break;
+    }
   }
   // ---- integrate
 #pragma unroll
