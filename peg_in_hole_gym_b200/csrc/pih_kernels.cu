@@ -328,13 +328,9 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
 void pih_destroy(pih_handle* h) {
   if (!h) return;
   if (h->h_action) cudaFreeHost(h->h_action);
-  if (h->h_obs) cudaFreeHost(h->h_obs);
-  if (h->h_reward) cudaFreeHost(h->h_reward);
-  if (h->h_done) cudaFreeHost(h->h_done);
+  if (h->h_obs) cudaFreeHost(h->h_obs);     // one pinned block: obs | reward | done
   if (h->d_action) cudaFree(h->d_action);
-  if (h->d_obs) cudaFree(h->d_obs);
-  if (h->d_reward) cudaFree(h->d_reward);
-  if (h->d_done) cudaFree(h->d_done);
+  if (h->d_obs) cudaFree(h->d_obs);         // one device block: obs | reward | done
   if (h->d_scene) cudaFree(h->d_scene);
   delete h;
 }
@@ -380,21 +376,23 @@ int pih_step(pih_handle* h, const float* action_dev, float* obs_dev, float* rewa
   return PIH_OK;
 }
 
+// staging for the host-buffer call: ONE pinned block and ONE device block holding [obs n*5 f32 | reward n f32 | done n u8],
+// so that the results come back in a single D2H copy
+static size_t out_bytes(size_t n) { return n * 5 * sizeof(float) + n * sizeof(float) + n; }
+
 static int ensure_staging(pih_handle* h) {
   if (h->h_action) return PIH_OK;
   size_t n = (size_t)h->P.n;
   cudaError_t ce = cudaMallocHost(&h->h_action, n * 6 * sizeof(float));
-  if (ce == cudaSuccess) ce = cudaMallocHost(&h->h_obs, n * 5 * sizeof(float));
-  if (ce == cudaSuccess) ce = cudaMallocHost(&h->h_reward, n * sizeof(float));
-  if (ce == cudaSuccess) ce = cudaMallocHost(&h->h_done, n);
+  if (ce == cudaSuccess) ce = cudaMallocHost(&h->h_obs, out_bytes(n));
   if (ce == cudaSuccess) ce = cudaMalloc(&h->d_action, n * 6 * sizeof(float));
-  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_obs, n * 5 * sizeof(float));
-  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_reward, n * sizeof(float));
-  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_done, n);
-  if (ce == cudaSuccess) ce = cudaMemset(h->d_obs, 0, n * 5 * sizeof(float));
-  if (ce == cudaSuccess) ce = cudaMemset(h->d_reward, 0, n * sizeof(float));
-  if (ce == cudaSuccess) ce = cudaMemset(h->d_done, 0, n);
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_obs, out_bytes(n));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_obs, 0, out_bytes(n));
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "staging allocation", ce);
+  h->h_reward = h->h_obs + n * 5;
+  h->h_done = reinterpret_cast<unsigned char*>(h->h_reward + n);
+  h->d_reward = h->d_obs + n * 5;
+  h->d_done = reinterpret_cast<unsigned char*>(h->d_reward + n);
   return PIH_OK;
 }
 
@@ -410,9 +408,7 @@ int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, floa
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "H2D", ce);
   rc = pih_step(h, h->d_action, h->d_obs, h->d_reward, h->d_done, stream);
   if (rc) return rc;
-  ce = cudaMemcpyAsync(h->h_obs, h->d_obs, n * 5 * sizeof(float), cudaMemcpyDeviceToHost, st);
-  if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->h_reward, h->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, st);
-  if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st);
+  ce = cudaMemcpyAsync(h->h_obs, h->d_obs, out_bytes(n), cudaMemcpyDeviceToHost, st);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "D2H", ce);
   if (obs_host) memcpy(obs_host, h->h_obs, n * 5 * sizeof(float));
