@@ -6,6 +6,12 @@
 
 namespace pih {
 
+// unroll factor of the PGS motor / limit row loops (1 = rolled: small loop body that stays in the L0 I-cache)
+#ifndef PIH_PGS_UNROLL
+#define PIH_PGS_UNROLL 9
+#endif
+constexpr int kPgsUnroll = PIH_PGS_UNROLL;
+
 template <int ARM> __host__ __device__ constexpr int sph_body_of(int s) {
   constexpr int tp[] = {PIH_PANDA_SPH_BODY_LIST};
   constexpr int tu[] = {PIH_UR5_SPH_BODY_LIST};
@@ -553,7 +559,7 @@ template <int ARM, int TASK> __device__ __noinline__ bool step_env(const SimPara
   for (int it = 0; it < P.solver_iters; ++it) {
     float res_a = 0.0f, res_f = 0.0f;
     if (arm_on) {
-#pragma unroll
+#pragma unroll kPgsUnroll
       for (int j = 0; j < nb; ++j) {
         float dl = fmaf(-dva[j], m_dinv[j], m_b[j]);
         float s = m_lam[j] + dl;
@@ -566,7 +572,7 @@ template <int ARM, int TASK> __device__ __noinline__ bool step_env(const SimPara
         for (int i = 0; i < nb; ++i) dva[i] = fmaf(Minv[i][j], dl, dva[i]);
       }
       if (l_on) {  // uniform-ish skip: most steps only the finger limit rows exist
-#pragma unroll
+#pragma unroll kPgsUnroll
         for (int j = 0; j < nb; ++j) {
 #pragma unroll
           for (int side = 0; side < 2; ++side) {
