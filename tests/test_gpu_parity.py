@@ -342,3 +342,45 @@ def test_camera_render_matches_oracle_and_full_size():
     env.reset()
     assert tuple(env.render('rgb_array').shape) == (2, 2, 300, 300, 4)
     env.close()
+
+
+@pytest.mark.parametrize("arm,task,fly", [("panda", "peg-in-hole", "banana"), ("ur5", "peg-in-hole", "banana"),
+                                          ("panda", "random-fly", "amicelli")])
+def test_randomised_states_fuzz_bit_exact(arm, task, fly):
+    """Fuzz: random (even unphysical) joint states, velocities and free-body poses injected into BOTH engines, then
+    40 steps of random actions - exercises limits, deep penetrations, table/hole/finger contacts, velocity clamps."""
+    n = 192
+    dt = 1.0 / 120.0 if task == "random-fly" else 1.0 / 240.0
+    sim, orc = _pair(n, arm=arm, task=task, fly_object=fly, dt=dt, offset=(2.0, 3.0, 0.0), seed=31, max_steps=25, auto_reset=True)
+    sim.reset(); orc.reset()
+    rng = np.random.default_rng(17)
+    w = orc.get_state()
+    flat = np.ascontiguousarray(w.transpose(1, 0, 2)).reshape(n, -1)
+    nq = 9 if arm == "panda" else 6
+    flat[:, ol.S_Q:ol.S_Q + nq] += rng.normal(0, 0.6, (n, nq)).astype(np.float32)
+    if arm == "panda":
+        flat[:, ol.S_Q + 7:ol.S_Q + 9] = rng.uniform(-0.01, 0.05, (n, 2))
+    flat[:, ol.S_QD:ol.S_QD + nq] = rng.normal(0, 2.0, (n, nq))
+    # free body near the gripper / table / hole, random orientation and twist
+    ee = orc.obs[:, 2:5] - sim.env_offsets().numpy()
+    where = rng.integers(0, 3, n)
+    pos = np.where(where[:, None] == 0, ee + rng.uniform(-0.04, 0.04, (n, 3)),
+                   np.where(where[:, None] == 1, np.array([0.5, -0.2, 0.2]) + rng.uniform(-0.04, 0.04, (n, 3)),
+                            np.stack([rng.uniform(-0.3, 0.3, n), rng.uniform(-0.7, -0.3, n), rng.uniform(-0.07, 0.05, n)], 1)))
+    flat[:, ol.S_PPOS:ol.S_PPOS + 3] = pos
+    q = rng.normal(size=(n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    flat[:, ol.S_PQUAT:ol.S_PQUAT + 4] = q
+    flat[:, ol.S_PVEL:ol.S_PVEL + 3] = rng.normal(0, 1.0, (n, 3))
+    flat[:, ol.S_PANG:ol.S_PANG + 3] = rng.normal(0, 10.0, (n, 3))
+    w2 = np.ascontiguousarray(flat.reshape(n, -1, 4).transpose(1, 0, 2)).astype(np.float32)
+    orc.set_state(w2)
+    sim.state.copy_(torch.from_numpy(w2))
+    acts = _random_actions(n, 4 if arm == "panda" else 6, 40, sim.env_offsets().numpy(), 5)
+    seen = 0
+    for t, a in enumerate(acts):
+        g = sim.step(torch.from_numpy(a).cuda())
+        c = orc.step(a)
+        assert np.array_equal(g[2].cpu().numpy(), c[2]) and np.array_equal(g[1].cpu().numpy(), c[1]), t
+        seen |= int(np.bitwise_or.reduce(sim.int_word(11).cpu().numpy() >> 8))
+    _assert_state_equal(sim, orc)
+    assert seen & 1, "table contacts expected"
