@@ -845,6 +845,22 @@ static void FN(collide)(const model* M, const simcfg* C, const envstate* S, cons
       FN(contact_push)(CS, &c);
     }
   }
+  /* (3b) free body vs arm collision spheres (hand, wrist, forearm): sphere centre against the free body's SDF.
+   *      Finger-tip spheres are skipped on the panda: the finger boxes of (3) already cover them. */
+  for (int s = 0; s < M->nsph; ++s) {
+    int body = M->sph_body[s];
+    if (body >= M->narm) continue;
+    v3 cw = FN(m3_v_add)(&F->Rw[body], M->sph_c[s], F->pw[body]);
+    v3 dd = FN(v3_sub)(cw, pfb);
+    real reach = M->fb_half.x + M->fb_half.y + M->fb_half.z + M->sph_r[s] + RC(PIH_CONTACT_MARGIN);
+    if (!(FN(v3_dot)(dd, dd) < reach * reach)) continue;
+    v3 nn;
+    real d = FN(fb_sdf)(M, Rfb, pfb, cw, &nn);
+    c.pair = PIH_PAIR_FB_ARM; c.has_fb = 1; c.arm_body = body;
+    c.n = FN(v3_make)(-nn.x, -nn.y, -nn.z);                  /* from the arm sphere into the free body */
+    c.p = FN(v3_axpy)(-M->sph_r[s], nn, cw); c.dist = d - M->sph_r[s]; c.mu = M->fb_mu * RC(PIH_MU_DEFAULT);
+    FN(contact_push)(CS, &c);
+  }
   /* (4) arm collision spheres vs table plane */
   for (int s = 0; s < M->nsph; ++s) {
     int body = M->sph_body[s];

@@ -33,6 +33,7 @@
 #define PIH_PAIR_PEG_FINGER1 4
 #define PIH_PAIR_PEG_FINGER2 8
 #define PIH_PAIR_ARM_TABLE 16
+#define PIH_PAIR_FB_ARM 32       /* free body vs arm collision spheres (hand / wrist links) */
 
 /* tasks / arms */
 #define PIH_TASK_PEG_IN_HOLE 0

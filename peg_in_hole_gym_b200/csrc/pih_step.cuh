@@ -230,6 +230,24 @@ template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvSta
       contact_push(CS, c);
     }
   }
+  // (3b) free body vs arm collision spheres (hand, wrist, forearm); finger-tip spheres are covered by the boxes of (3)
+  sfor<0, ArmGeom<ARM>::NSPH>([&](auto s_) {
+    constexpr int s = decltype(s_)::value;
+    constexpr int body = sph_body_of<ARM>(s);
+    if constexpr (body < ArmDims<ARM>::NARM) {
+      v3 cw = mv_add(F.Rw[body], ld3(T.sph_c[s]), F.pw[body]);
+      v3 dd = vsub(cw, pfb);
+      float reach = P.fb_half[0] + P.fb_half[1] + P.fb_half[2] + T.sph_r[s] + (float)PIH_CONTACT_MARGIN;
+      if (vdot(dd, dd) < reach * reach) {
+        v3 nn;
+        float d = fb_sdf<TASK>(P, Rfb, pfb, cw, nn);
+        c.pair = PIH_PAIR_FB_ARM; c.has_fb = 1; c.arm_body = body;
+        c.n = mk(-nn.x, -nn.y, -nn.z);
+        c.p = vaxpy(-T.sph_r[s], nn, cw); c.dist = d - T.sph_r[s]; c.mu = P.fb_mu * (float)PIH_MU_DEFAULT;
+        contact_push(CS, c);
+      }
+    }
+  });
   // (4) arm collision spheres vs table plane
 #pragma unroll
   for (int s = 0; s < ArmGeom<ARM>::NSPH; ++s) {
