@@ -112,6 +112,126 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOC
   }
 }
 
+
+// ---- warp-specialised variants for small batches (one warp per scheduler is the limit of thread-per-env latency):
+// a CTA of 64 threads owns 32 envs; warp 0 runs apply_action (FK -> vel_constraint -> 20 IK iterations) while warp 1
+// runs the target-independent half of stepSimulation (ABA, M^-1, narrow phase, contact rows); the joint targets cross
+// through a shared-memory mailbox at the motor rows.  Same arithmetic as k_step / k_rollout, bit for bit.  Every lane
+// executes the whole code (frozen / padding lanes compute on a copy and never commit) so that both warps reach the
+// barriers converged.
+template <int ARM, int TASK> PIH_D void mailbox_put(float (*mb)[32], int lane, const float* qs, const float* kpc, const float* mfc, bool fsm_done,
+                                                     const EnvState& S) {
+  constexpr int nb = ArmDims<ARM>::NB;
+#pragma unroll
+  for (int j = 0; j < nb; ++j) { mb[PIH_MB_QSTAR + j][lane] = qs[j]; mb[PIH_MB_KP + j][lane] = kpc[j]; mb[PIH_MB_MAXF + j][lane] = mfc[j]; }
+  mb[PIH_MB_FSM_DONE][lane] = fsm_done ? 1.0f : 0.0f;
+  mb[PIH_MB_FSM_STATE][lane] = __int_as_float(S.fsm_state); mb[PIH_MB_FSM_T][lane] = __int_as_float(S.fsm_t);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) mb[PIH_MB_MTGT + k][lane] = S.mtgt[k];
+}
+
+template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(SimParams P, const float* __restrict__ action, float* __restrict__ obs,
+                                                                          float* __restrict__ reward, unsigned char* __restrict__ done) {
+  __shared__ float mb[PIH_MB_WORDS][32];
+  constexpr int A = ArmDims<ARM>::ADIM, nb = ArmDims<ARM>::NB;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
+  const int ec = e < P.n ? e : P.n - 1;
+  EnvState S;
+  load_state(P, ec, S);
+  const bool active = (e < P.n) && !(S.flags & PIH_FLAG_DONE);
+  const v3 off = env_offset(P, ec);
+  FK<ARM> F;
+  fk<ARM, nb>(S.q, F);
+  float qs[nb], kpc[nb], mfc[nb];
+  if (w == 0) {
+    float a[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int k = 0; k < A; ++k) a[k] = __ldg(&action[(size_t)A * ec + k]);
+    const bool fd = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc);
+    mailbox_put<ARM, TASK>(mb, lane, qs, kpc, mfc, fd, S);
+    __syncthreads();
+    return;
+  }
+  float o[5], r;
+  unsigned char d;
+  step_back_ws<ARM, TASK>(P, S, F, qs, kpc, mfc, false, mb, lane, active, off, (unsigned)(P.env_id_base + ec), o, r, d);
+  if (!active) return;
+  store_state(P, e, S);
+  if (obs) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) obs[5 * (size_t)e + k] = o[k];
+  }
+  if (reward) reward[e] = r;
+  if (done) done[e] = d;
+}
+
+template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_rollout_ws(SimParams P, int steps, float* __restrict__ obs, float* __restrict__ reward,
+                                                                             unsigned char* __restrict__ done, unsigned long long* __restrict__ counters) {
+  __shared__ float mb[PIH_MB_WORDS][32];
+  __shared__ float4 st[PIH_STATE_F4][32];   // dynamics warp -> action warp: the new state after every step
+  constexpr int A = ArmDims<ARM>::ADIM, nb = ArmDims<ARM>::NB;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int e = blockIdx.x * 32 + lane;
+  const int ec = e < P.n ? e : P.n - 1;
+  EnvState S;
+  load_state(P, ec, S);
+  const v3 off = env_offset(P, ec);
+  const unsigned gid = (unsigned)(P.env_id_base + ec);
+  float o[5] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, r = 0.0f;
+  unsigned char d = 0;
+  bool any = false;
+  unsigned nsteps = 0, ndone = 0;
+  for (int t = 0; t < steps; ++t) {
+    const bool active = (e < P.n) && !(S.flags & PIH_FLAG_DONE);
+    FK<ARM> F;
+    fk<ARM, nb>(S.q, F);
+    float qs[nb], kpc[nb], mfc[nb];
+    if (w == 0) {
+      float u[8], a[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f}, u0[4];
+      rng4(P, gid, P.global_step + (unsigned)t, PIH_STREAM_ACTION, u0);
+      u[0] = u0[0]; u[1] = u0[1]; u[2] = u0[2]; u[3] = u0[3];
+      if (A > 4) { rng4(P, gid, P.global_step + (unsigned)t, PIH_STREAM_ACTION + 1, u0); u[4] = u0[0]; u[5] = u0[1]; u[6] = u0[2]; u[7] = u0[3]; }
+#pragma unroll
+      for (int k = 0; k < A; ++k) a[k] = fmaf(u[k], 2.0f, -1.0f);
+      if (!P.action_frame_env) { a[0] += off.x; a[1] += off.y; a[2] += off.z; }
+      const bool fd = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc);
+      mailbox_put<ARM, TASK>(mb, lane, qs, kpc, mfc, fd, S);
+      __syncthreads();   // A: targets ready
+      __syncthreads();   // B: new state published by the dynamics warp
+      load_state_smem(st, lane, S);
+    } else {
+      float o2[5], r2;
+      unsigned char d2;
+      step_back_ws<ARM, TASK>(P, S, F, qs, kpc, mfc, false, mb, lane, active, off, gid, o2, r2, d2);   // contains barrier A
+      if (active) {
+        any = true;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) o[k] = o2[k];
+        r = r2; d = d2;
+        nsteps += 1; ndone += d2;
+      }
+      store_state_smem(st, lane, S);
+      __syncthreads();   // B
+    }
+  }
+  if (w == 0 || e >= P.n) return;
+  store_state(P, e, S);
+  if (any) {
+    if (obs) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) obs[5 * (size_t)e + k] = o[k];
+    }
+    if (reward) reward[e] = r;
+    if (done) done[e] = d;
+  }
+  if (counters) {
+    const unsigned m = __activemask();
+    unsigned ws = __reduce_add_sync(m, nsteps), wd = __reduce_add_sync(m, ndone);
+    if (lane == (unsigned)(__ffs(m) - 1)) { atomicAdd(&counters[0], (unsigned long long)ws); atomicAdd(&counters[1], (unsigned long long)wd); }
+  }
+}
+
 template <int ARM, int TASK> __global__ void __launch_bounds__(128) k_ik(SimParams P, const float* __restrict__ action, float* __restrict__ qtarget) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.n) return;
@@ -180,6 +300,7 @@ struct pih_handle {
   SimParams P;
   int was_reset;
   int block;
+  int ws;  // warp-specialised kernels for small batches
   char err[256];
   // staging for pih_step_host
   float *h_action, *h_obs, *h_reward;
@@ -315,6 +436,9 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   P.fb_iinv[0] = (float)(1.0 / ix); P.fb_iinv[1] = (float)(1.0 / iy); P.fb_iinv[2] = (float)(1.0 / iz);
   P.state = reinterpret_cast<float4*>(state_dev);
   h->block = 32;
+  h->ws = (P.n <= 148 * 32 * 2) ? 1 : 0;   // up to two 64-thread CTAs per SM: every warp still has a scheduler to itself
+  const char* wse = getenv("PIH_WS");
+  if (wse) h->ws = atoi(wse) ? 1 : 0;
   const char* bs = getenv("PIH_BLOCK");
   if (bs) { int b = atoi(bs); if (b == 32 || b == 64 || b == 128) h->block = b; }
   k_init_state<<<(P.n + 127) / 128, 128>>>(P.state, P.n);
@@ -349,6 +473,18 @@ const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null hand
     if ((h)->P.arm == PIH_ARM_PANDA) LAUNCH_T(kern, PIH_ARM_PANDA, h, st, __VA_ARGS__); \
     else LAUNCH_T(kern, PIH_ARM_UR5, h, st, __VA_ARGS__);                         \
   } while (0)
+#define LAUNCH_WS_T(kern, ARMV, h, st, ...)                                                                             \
+  do {                                                                                                                 \
+    if ((h)->P.task == PIH_TASK_PEG_IN_HOLE) kern<ARMV, PIH_TASK_PEG_IN_HOLE><<<gridw_, 64, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
+    else if ((h)->P.task == PIH_TASK_RANDOM_FLY) kern<ARMV, PIH_TASK_RANDOM_FLY><<<gridw_, 64, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
+    else kern<ARMV, PIH_TASK_SCRIPTED><<<gridw_, 64, 0, (cudaStream_t)(st)>>>(__VA_ARGS__);                            \
+  } while (0)
+#define LAUNCH_WS(kern, h, st, ...)                                               \
+  do {                                                                            \
+    int gridw_ = ((h)->P.n + 31) / 32;                                            \
+    if ((h)->P.arm == PIH_ARM_PANDA) LAUNCH_WS_T(kern, PIH_ARM_PANDA, h, st, __VA_ARGS__); \
+    else LAUNCH_WS_T(kern, PIH_ARM_UR5, h, st, __VA_ARGS__);                      \
+  } while (0)
 #define LAUNCH_ARM(kern, h, st, ...)                                              \
   do {                                                                            \
     int grid_ = ((h)->P.n + (h)->block - 1) / (h)->block;                         \
@@ -369,7 +505,8 @@ int pih_reset(pih_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stre
 int pih_step(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream) {
   if (!h || !action_dev) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "step() before reset()", cudaSuccess);
-  LAUNCH(k_step, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev);
+  if (h->ws) { LAUNCH_WS(k_step_ws, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev); }
+  else { LAUNCH(k_step, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev); }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_step launch", ce);
   h->P.global_step += 1;
@@ -420,7 +557,8 @@ int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, floa
 int pih_rollout(pih_handle* h, int32_t steps, float* obs_dev, float* reward_dev, uint8_t* done_dev, unsigned long long* counters_dev, void* stream) {
   if (!h || steps < 0) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "rollout() before reset()", cudaSuccess);
-  LAUNCH(k_rollout, h, stream, h->P, (int)steps, obs_dev, reward_dev, done_dev, counters_dev);
+  if (h->ws) { LAUNCH_WS(k_rollout_ws, h, stream, h->P, (int)steps, obs_dev, reward_dev, done_dev, counters_dev); }
+  else { LAUNCH(k_rollout, h, stream, h->P, (int)steps, obs_dev, reward_dev, done_dev, counters_dev); }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_rollout launch", ce);
   h->P.global_step += (unsigned)steps;

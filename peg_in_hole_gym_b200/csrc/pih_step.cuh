@@ -432,317 +432,46 @@ template <int ARM, int TASK> PIH_D bool apply_action(const SimParams& P, EnvStat
   return false;
 }
 
+// Mailbox from the action-application warp to the dynamics warp of the warp-specialised kernels (one column per lane).
+#define PIH_MB_WORDS 40
+#define PIH_MB_QSTAR 0
+#define PIH_MB_KP 9
+#define PIH_MB_MAXF 18
+#define PIH_MB_FSM_DONE 27
+#define PIH_MB_FSM_STATE 28
+#define PIH_MB_FSM_T 29
+#define PIH_MB_MTGT 30
+
+// Everything of one env.step after apply_action: stepSimulation (ABA, M^-1, contacts, PGS, integration) and get_info.
+// The body lives in pih_step_body.inc and is instantiated twice: the classic single-warp order and the warp-specialised
+// order, in which the joint targets arrive from the sibling warp through the shared-memory mailbox `mb` at the one
+// point where they are needed (motor rows), after this warp has already done the target-independent work.
+template <int ARM, int TASK>
+__device__ __forceinline__ void step_back(const SimParams& P, EnvState& S, const FK<ARM>& F, float* qstar, float* kpc, float* mfc, bool fsm_done,
+                                          bool commit, v3 off, unsigned gid, float (&obs)[5], float& reward, unsigned char& done) {
+#define PIH_STEP_WS 0
+#include "pih_step_body.inc"
+#undef PIH_STEP_WS
+}
+template <int ARM, int TASK>
+__device__ __forceinline__ void step_back_ws(const SimParams& P, EnvState& S, const FK<ARM>& F, float* qstar, float* kpc, float* mfc, bool fsm_done,
+                                             float (*mb)[32], int lane, bool commit, v3 off, unsigned gid, float (&obs)[5], float& reward,
+                                             unsigned char& done) {
+#define PIH_STEP_WS 1
+#include "pih_step_body.inc"
+#undef PIH_STEP_WS
+}
+
 // One env.step for one env.  Returns false if the env was frozen (done and not reset): outputs untouched.
 template <int ARM, int TASK> __device__ __noinline__ bool step_env(const SimParams& P, EnvState& S, const float* action, v3 off, unsigned gid,
-                                                         float (&obs)[5], float& reward, unsigned char& done) {
+                                                              float (&obs)[5], float& reward, unsigned char& done) {
   if (S.flags & PIH_FLAG_DONE) return false;
-  constexpr int nb = ArmDims<ARM>::NB, na = ArmDims<ARM>::NARM;
-  const ArmTables& T = c_arm[ARM];
-  const float dt = P.dt, idt = P.idt;
+  constexpr int nb = ArmDims<ARM>::NB;
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
   float qstar[nb], kpc[nb], mfc[nb];
   const bool fsm_done = apply_action<ARM, TASK>(P, S, F, action, off, qstar, kpc, mfc);
-  // ---- unconstrained accelerations
-  float tau[nb];
-#pragma unroll
-  for (int i = 0; i < nb; ++i) tau[i] = -(T.damp[i] * S.qd[i]);
-  ABA<ARM> AB;
-  aba<ARM>(F, S.qd, tau, (float)PIH_GRAVITY, AB);
-  float Minv[nb][nb];
-  for (int j = 0; j < nb; ++j) {
-    float col[nb];
-    minv_column<ARM>(F, AB, j, col);
-#pragma unroll
-    for (int i = 0; i < nb; ++i) Minv[i][j] = col[i];
-  }
-  float vs[nb];
-#pragma unroll
-  for (int i = 0; i < nb; ++i) vs[i] = fmaf(dt, AB.qdd[i], S.qd[i]);
-  m3 Rfb = quat_to_m3(S.pquat);
-  v3 fv = mk(S.pvel[0], S.pvel[1], fmaf(dt, (float)(-PIH_GRAVITY), S.pvel[2]));
-  v3 fw = mk(S.pang[0], S.pang[1], S.pang[2]);
-  {
-    v3 wb = mTv(Rfb, fw);
-    v3 Iw = mk(P.fb_idiag[0] * wb.x, P.fb_idiag[1] * wb.y, P.fb_idiag[2] * wb.z);
-    v3 g = vcross(wb, Iw);
-    v3 al = mk(-(g.x * P.fb_iinv[0]), -(g.y * P.fb_iinv[1]), -(g.z * P.fb_iinv[2]));
-    fw = clamp_norm(vaxpy(dt, mv(Rfb, al), fw));
-  }
-  m3 Iinv;
-  {
-    m3 Tm;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) { Tm.m[r][0] = Rfb.m[r][0] * P.fb_iinv[0]; Tm.m[r][1] = Rfb.m[r][1] * P.fb_iinv[1]; Tm.m[r][2] = Rfb.m[r][2] * P.fb_iinv[2]; }
-    Iinv = mmulT(Tm, Rfb);
-  }
-  const float im = P.fb_im;
-  // ---- motor + limit rows
-  float m_dinv[nb], m_b[nb], m_lam[nb], m_max[nb], l_b[2][nb], l_lam[2][nb];
-  unsigned l_on = 0u;  // bit 2j: lower limit row of joint j present, bit 2j+1: upper
-#pragma unroll
-  for (int j = 0; j < nb; ++j) {
-    // targets outside the URDF limits are unreachable: aim at the limit instead of fighting the limit row
-    float qt = qstar[j];
-    qt = (qt < T.lo[j]) ? T.lo[j] : ((qt > T.hi[j]) ? T.hi[j] : qt);
-    float vstar = kpc[j] * (qt - S.q[j]) * idt;
-    m_dinv[j] = 1.0f / Minv[j][j];
-    m_b[j] = (vstar - vs[j]) * m_dinv[j];
-    m_lam[j] = 0.0f;
-    m_max[j] = mfc[j] * dt;
-    // a limit row exists only if the joint can reach that limit this step (see oracle for the rule)
-    float glo = S.q[j] - T.lo[j], ghi = T.hi[j] - S.q[j];
-    float vdn = fmaxf(fmaxf(-vstar, -vs[j]), 0.0f), vup = fmaxf(fmaxf(vstar, vs[j]), 0.0f);
-    l_on |= (glo < fmaf(vdn, dt, 0.005f) ? 1u : 0u) << (2 * j);
-    l_on |= (ghi < fmaf(vup, dt, 0.005f) ? 1u : 0u) << (2 * j + 1);
-    l_lam[0][j] = l_lam[1][j] = 0.0f;
-    float tlo = (glo > 0.0f) ? -(glo * idt) : -((float)PIH_ERP * glo * idt);
-    float thi = (ghi > 0.0f) ? -(ghi * idt) : -((float)PIH_ERP * ghi * idt);
-    l_b[0][j] = (tlo - vs[j]) * m_dinv[j];
-    l_b[1][j] = (thi + vs[j]) * m_dinv[j];
-  }
-  // ---- contacts
-  ContactSet CS;
-  collide<ARM, TASK>(P, S, F, Rfb, CS);
-  CRow<ARM> rows[PIH_MAXC];
-  int pairmask = 0;
-  bool arm_contacts = false, coupled = false;
-  v3 pfb = mk(S.ppos[0], S.ppos[1], S.ppos[2]);
-  for (int k = 0; k < CS.n; ++k) {
-    const Contact& c = CS.c[k];
-    CRow<ARM>& r = rows[k];
-    pairmask |= c.pair;
-    arm_contacts = arm_contacts || (c.arm_body >= 0);
-    coupled = coupled || (c.has_fb && c.arm_body >= 0);
-    r.has_fb = c.has_fb; r.arm_body = c.arm_body; r.mu = c.mu;
-    r.dir[0] = c.n;
-    plane_space(c.n, r.dir[1], r.dir[2]);
-    v3 rr = vsub(c.p, pfb);
-    unsigned anc = (c.arm_body >= 0) ? anc_rt<ARM>(c.arm_body) : 0u;
-    for (int d = 0; d < 3; ++d) {
-      float diag = 0.0f, vrel = 0.0f;
-      if (c.has_fb) {
-        r.jang[d] = vcross(rr, r.dir[d]);
-        r.mang[d] = mv(Iinv, r.jang[d]);
-        diag = im + vdot(r.jang[d], r.mang[d]);
-        vrel = vdot(r.dir[d], fv) + vdot(r.jang[d], fw);
-      }
-      if (c.arm_body >= 0) {
-        float sg = c.has_fb ? -1.0f : 1.0f;
-        float jrow[nb];
-#pragma unroll
-        for (int j = 0; j < nb; ++j) {
-          float v = 0.0f;
-          if ((anc >> j) & 1u) {
-            v3 z = mcol(F.Rw[j], 2);
-            if (jtype_of<ARM>(j) == 0) v = vdot(r.dir[d], vcross(z, vsub(c.p, F.pw[j])));
-            else v = vdot(r.dir[d], z);
-            v = sg * v;
-          }
-          jrow[j] = v;
-          r.ja[d][j] = v;
-        }
-        float da = 0.0f, va = 0.0f;
-        float mrow_[nb];
-#pragma unroll
-        for (int i = 0; i < nb; ++i) {
-          float s = 0.0f;
-#pragma unroll
-          for (int j = 0; j < nb; ++j) s = fmaf(Minv[i][j], jrow[j], s);
-          mrow_[i] = s;
-          r.ma[d][i] = s;
-        }
-#pragma unroll
-        for (int j = 0; j < nb; ++j) { da = fmaf(jrow[j], mrow_[j], da); va = fmaf(jrow[j], vs[j], va); }
-        diag = diag + da;
-        vrel = vrel + va;
-      }
-      r.dinv[d] = 1.0f / diag;
-      r.diag[d] = diag;
-      float tv = 0.0f;
-      if (d == 0) tv = (c.dist > 0.0f) ? -(c.dist * idt) : -((float)PIH_ERP * c.dist * idt);
-      r.b[d] = (tv - vrel) * r.dinv[d];
-      r.lam[d] = 0.0f;
-    }
-  }
-  // ---- projected Gauss-Seidel: motors, limits, contact normals, contact friction.  Early exit on PyBullet's
-  //      solverResidualThreshold: largest squared velocity change (deltaImpulse / jacDiagABInv)^2 of the iteration,
-  //      evaluated per simulation island (arm island / free-body island; merged by a finger<->free-body contact).
-  float dva[nb];
-#pragma unroll
-  for (int j = 0; j < nb; ++j) dva[j] = 0.0f;
-  v3 dvl = mk(0.0f, 0.0f, 0.0f), dvw = dvl;
-  const int ncon = CS.n;
-  bool arm_on = true, fb_on = true;
-  for (int it = 0; it < P.solver_iters; ++it) {
-    float res_a = 0.0f, res_f = 0.0f;
-    if (arm_on) {
-#pragma unroll kPgsUnroll
-      for (int j = 0; j < nb; ++j) {
-        float dl = fmaf(-dva[j], m_dinv[j], m_b[j]);
-        float s = m_lam[j] + dl;
-        s = fminf(fmaxf(s, -m_max[j]), m_max[j]);
-        dl = s - m_lam[j];
-        m_lam[j] = s;
-        float rv = dl * Minv[j][j];
-        res_a = fmaxf(res_a, rv * rv);
-#pragma unroll
-        for (int i = 0; i < nb; ++i) dva[i] = fmaf(Minv[i][j], dl, dva[i]);
-      }
-      if (l_on) {  // uniform-ish skip: most steps only the finger limit rows exist
-#pragma unroll kPgsUnroll
-        for (int j = 0; j < nb; ++j) {
-#pragma unroll
-          for (int side = 0; side < 2; ++side) {
-            if (!((l_on >> (2 * j + side)) & 1u)) continue;
-            float sg = side ? -1.0f : 1.0f;
-            float dl = fmaf(-(sg * dva[j]), m_dinv[j], l_b[side][j]);
-            float s = l_lam[side][j] + dl;
-            s = fmaxf(s, 0.0f);
-            dl = (s - l_lam[side][j]) * sg;
-            l_lam[side][j] = s;
-            float rv = dl * Minv[j][j];
-            res_a = fmaxf(res_a, rv * rv);
-#pragma unroll
-            for (int i = 0; i < nb; ++i) dva[i] = fmaf(Minv[i][j], dl, dva[i]);
-          }
-        }
-      }
-    }
-    if (!arm_contacts) {
-      // common case: every contact is free body vs static geometry -> no per-row type branches, no arm coupling
-      if (fb_on) {
-        for (int k = 0; k < ncon; ++k) {
-          CRow<ARM>& r = rows[k];
-          float rel = vdot(r.dir[0], dvl) + vdot(r.jang[0], dvw);
-          float dl = fmaf(-rel, r.dinv[0], r.b[0]);
-          float s = fmaxf(r.lam[0] + dl, 0.0f);
-          dl = s - r.lam[0];
-          r.lam[0] = s;
-          float rv = dl * r.diag[0];
-          res_f = fmaxf(res_f, rv * rv);
-          dvl = vaxpy(dl * im, r.dir[0], dvl);
-          dvw = vaxpy(dl, r.mang[0], dvw);
-        }
-        for (int k = 0; k < ncon; ++k) {
-          CRow<ARM>& r = rows[k];
-          const float lim = r.mu * r.lam[0];
-#pragma unroll
-          for (int d = 1; d < 3; ++d) {
-            float rel = vdot(r.dir[d], dvl) + vdot(r.jang[d], dvw);
-            float dl = fmaf(-rel, r.dinv[d], r.b[d]);
-            float s = fminf(fmaxf(r.lam[d] + dl, -lim), lim);
-            dl = s - r.lam[d];
-            r.lam[d] = s;
-            float rv = dl * r.diag[d];
-            res_f = fmaxf(res_f, rv * rv);
-            dvl = vaxpy(dl * im, r.dir[d], dvl);
-            dvw = vaxpy(dl, r.mang[d], dvw);
-          }
-        }
-      }
-    } else {
-      for (int pass = 0; pass < 2; ++pass)
-        for (int k = 0; k < ncon; ++k) {
-          CRow<ARM>& r = rows[k];
-          const bool is_fb = r.has_fb && r.arm_body < 0;
-          if (!coupled && !(is_fb ? fb_on : arm_on)) continue;
-          for (int d = (pass ? 1 : 0); d < (pass ? 3 : 1); ++d) {
-            float rel = 0.0f;
-            if (r.has_fb) rel = vdot(r.dir[d], dvl) + vdot(r.jang[d], dvw);
-            if (r.arm_body >= 0) {
-              float ra = 0.0f;
-#pragma unroll
-              for (int j = 0; j < nb; ++j) ra = fmaf(r.ja[d][j], dva[j], ra);
-              rel = rel + ra;
-            }
-            float dl = fmaf(-rel, r.dinv[d], r.b[d]);
-            float s = r.lam[d] + dl;
-            if (d == 0) s = fmaxf(s, 0.0f);
-            else {
-              float lim = r.mu * r.lam[0];
-              s = fminf(fmaxf(s, -lim), lim);
-            }
-            dl = s - r.lam[d];
-            r.lam[d] = s;
-            float rv = dl * r.diag[d];
-            if (is_fb) res_f = fmaxf(res_f, rv * rv); else res_a = fmaxf(res_a, rv * rv);
-            if (r.has_fb) { dvl = vaxpy(dl * im, r.dir[d], dvl); dvw = vaxpy(dl, r.mang[d], dvw); }
-            if (r.arm_body >= 0) {
-#pragma unroll
-              for (int j = 0; j < nb; ++j) dva[j] = fmaf(r.ma[d][j], dl, dva[j]);
-            }
-          }
-        }
-    }
-    if (coupled) {
-      if (fmaxf(res_a, res_f) <= P.solver_residual) break;
-    } else {
-      if (res_a <= P.solver_residual) arm_on = false;
-      if (res_f <= P.solver_residual) fb_on = false;
-      if (!arm_on && !fb_on) break;
-    }
-  }
-  // ---- integrate
-#pragma unroll
-  for (int j = 0; j < nb; ++j) {
-    float v = vs[j] + dva[j];
-    v = (v > (float)PIH_MAX_COORD_VEL) ? (float)PIH_MAX_COORD_VEL : ((v < (float)(-PIH_MAX_COORD_VEL)) ? (float)(-PIH_MAX_COORD_VEL) : v);
-    S.qd[j] = v;
-    S.q[j] = fmaf(dt, S.qd[j], S.q[j]);
-  }
-  fv = clamp_norm(vadd(fv, dvl));
-  fw = clamp_norm(vadd(fw, dvw));
-  S.pvel[0] = fv.x; S.pvel[1] = fv.y; S.pvel[2] = fv.z;
-  S.pang[0] = fw.x; S.pang[1] = fw.y; S.pang[2] = fw.z;
-  S.ppos[0] = fmaf(dt, fv.x, S.ppos[0]); S.ppos[1] = fmaf(dt, fv.y, S.ppos[1]); S.ppos[2] = fmaf(dt, fv.z, S.ppos[2]);
-  {
-    float w2 = vdot(fw, fw);
-    float wn = sqrtf(w2);
-    float ha = 0.5f * dt * wn;
-    float sh, ch, k;
-    det_sincos(ha, sh, ch);
-    if (wn > 1e-6f) k = sh / wn; else k = 0.5f * dt;
-    float dq[4] = {fw.x * k, fw.y * k, fw.z * k, ch}, nq[4];
-    quat_mul(dq, S.pquat, nq);
-    float n2 = fmaf(nq[3], nq[3], fmaf(nq[2], nq[2], fmaf(nq[1], nq[1], nq[0] * nq[0])));
-    float in = 1.0f / sqrtf(n2);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) S.pquat[i] = nq[i] * in;
-  }
-  S.step += 1;
-  // ---- get_info
-  float rew = 0.0f;
-  int success = 0;
-  FK<ARM> F2;
-  v3 pee2; m3 Ree2;
-  fk<ARM, nb>(S.q, F2);
-  ee_pose<ARM>(F2, pee2, Ree2);
-  if (TASK != PIH_TASK_RANDOM_FLY) {
-    v3 d = mk(S.ppos[0] - (float)PIH_HOLE_X, S.ppos[1] - (float)PIH_HOLE_Y, S.ppos[2] - (float)PIH_HOLE_Z);
-    success = vdot(d, d) < (float)(PIH_SUCCESS_RADIUS * PIH_SUCCESS_RADIUS);
-  } else {
-    v3 d = mk(S.ppos[0] - pee2.x, S.ppos[1] - pee2.y, S.ppos[2] - pee2.z);
-    success = vdot(d, d) < (float)(PIH_SUCCESS_RADIUS * PIH_SUCCESS_RADIUS);
-  }
-  rew = success ? 1.0f : 0.0f;
-  int dn = success || (P.max_steps > 0 && S.step >= P.max_steps);
-  if (TASK == PIH_TASK_RANDOM_FLY && (pairmask & PIH_PAIR_PEG_TABLE)) dn = 1;
-  if (TASK == PIH_TASK_SCRIPTED) dn = fsm_done || (P.max_steps > 0 && S.step >= P.max_steps);
-  S.flags = (dn ? PIH_FLAG_DONE : 0) | (success ? PIH_FLAG_SUCCESS : 0) | (pairmask << PIH_PAIR_SHIFT);
-  reward = rew;
-  done = (unsigned char)dn;
-  if (dn && P.auto_reset) {
-    int keep = S.flags & ~PIH_FLAG_DONE;
-    S.episode += 1;
-    reset_env<ARM, TASK>(P, S, gid);
-    S.flags = keep & ~0xff;
-    observe<ARM>(S, off, obs);
-  } else {
-    obs[0] = (nb > na) ? S.q[na < PIH_NB_MAX ? na : 0] : 0.0f;
-    obs[1] = (nb > na + 1) ? S.q[(na + 1) < PIH_NB_MAX ? na + 1 : 0] : 0.0f;
-    obs[2] = pee2.x + off.x; obs[3] = pee2.y + off.y; obs[4] = pee2.z + off.z;
-  }
+  step_back<ARM, TASK>(P, S, F, qstar, kpc, mfc, fsm_done, true, off, gid, obs, reward, done);
   return true;
 }
 

@@ -384,3 +384,34 @@ def test_randomised_states_fuzz_bit_exact(arm, task, fly):
         seen |= int(np.bitwise_or.reduce(sim.int_word(11).cpu().numpy() >> 8))
     _assert_state_equal(sim, orc)
     assert seen & 1, "table contacts expected"
+
+
+@pytest.mark.parametrize("arm,task", [("panda", "peg-in-hole"), ("ur5", "peg-in-hole"), ("panda", "random-fly"),
+                                      ("panda", "peg-in-hole-scripted")])
+def test_classic_and_warp_specialised_kernels_agree(arm, task, monkeypatch):
+    """Small batches run the warp-specialised kernels (k_step_ws / k_rollout_ws: apply_action and the dynamics
+    prologue in two warps), large ones the classic single-warp kernels.  Both must give the oracle's bits."""
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    n = 100                                              # not a multiple of 32: padding lanes in the last CTA
+    kw = dict(task=task, arm=arm, offset=(2.0, 3.0, 0.0), seed=6, max_steps=0 if "scripted" in task else 30,
+              auto_reset="scripted" not in task, dt=1.0 / 120.0 if task == "random-fly" else 1.0 / 240.0)
+    sims = {}
+    for ws in ("0", "1"):
+        monkeypatch.setenv("PIH_WS", ws)
+        sims[ws] = BatchedSim(n, device=0, **kw)
+        sims[ws].reset()
+    orc = ol.Oracle(ol.make_config(n, task={"peg-in-hole": 0, "random-fly": 1, "peg-in-hole-scripted": 2}[task],
+                                   arm={"panda": 0, "ur5": 1}[arm], offset=kw["offset"], seed=6, max_steps=kw["max_steps"],
+                                   auto_reset=int(kw["auto_reset"]), dt=kw["dt"]))
+    orc.reset()
+    acts = _random_actions(n, 4 if arm == "panda" else 6, 45, sims["0"].env_offsets().numpy(), 9)
+    for a in acts:                                       # per-step launches
+        for sm in sims.values():
+            sm.step(torch.from_numpy(a).cuda())
+        orc.step(a)
+    for sm in sims.values():                             # then the rollout kernels
+        sm.rollout(70)
+    orc.rollout(70)
+    assert torch.equal(sims["0"].state, sims["1"].state)
+    assert torch.equal(sims["0"].obs, sims["1"].obs) and torch.equal(sims["0"].done, sims["1"].done)
+    _assert_state_equal(sims["1"], orc)
