@@ -39,8 +39,8 @@ SEED = 0
 # algorithmic cost per env-step (SURVEY.md 8d formula)
 BYTES_PER_ENV_STEP = 2 * 192 + 16 + 20 + 4 + 1   # float4-SoA state read+write (12 slots), action, obs, reward, done
 FLOPS_BULLET_DEFAULT = 2.2e5                       # I_ik=20, I_pgs=50, n=9, R=33
-NCU_EXECUTED_FLOPS_PER_ENV_STEP = 4.41e4          # ncu: (2*FFMA + FMUL + FADD thread-instructions) per launch / 4096 envs (profiles/)
-NCU_TRAFFIC_BYTES = 1030144                         # k_step<panda>, 4096 envs: DRAM read 1.03 MB + write 0 B per launch (profiles/r01_kstep_ncu_full_final.csv)
+NCU_EXECUTED_FLOPS_PER_ENV_STEP = 4.51e4          # ncu: (2*FFMA + FMUL + FADD thread-instructions) per launch / 4096 envs (profiles/)
+NCU_TRAFFIC_BYTES = 1016832                         # k_step_ws<panda>, 4096 envs: DRAM read 1.02 MB + write 0 B per launch (profiles/r01_kstep_ws_ncu_full.csv)
 
 
 def flops_per_env_step(n=9, na=7, i_ik=20, i_pgs=50, rows=17):
@@ -318,7 +318,7 @@ def main():
             "gpu_launches": args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (ach_tf / peak_tf) if peak_tf else None, "traffic": NCU_TRAFFIC_BYTES if (args.arm == "panda" and n == ENVS_PER_GPU) else None,
-                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_kstep_ncu_full_final.csv",
+                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_kstep_ws_ncu_full.csv",
                          "peak_source": "in-run FFMA probe (pih_measure_fp32_peak); FP32 pipe is not in MEASURED_PEAKS.json",
                          "flops_per_env_step": f_run, "flops_per_env_step_bullet_default": FLOPS_BULLET_DEFAULT,
                          "executed_flops_per_env_step": NCU_EXECUTED_FLOPS_PER_ENV_STEP,
@@ -326,7 +326,7 @@ def main():
                          "frac_executed": (NCU_EXECUTED_FLOPS_PER_ENV_STEP * n / kern_s / 1e12 / peak_tf) if peak_tf else None,
                          "note": "achieved/frac use SURVEY 8(d)'s algorithmic FLOP model; *_executed use the FP32 thread-instructions ncu counted "
                                  "(the implementation skips structural zeros and reuses the ABA factorisation, so it executes ~3x fewer)",
-                         "kernel": "pih::k_step<panda>", "kernel_us": kern_s * 1e6,
+                         "kernel": ("pih::k_step_ws" if n <= 148 * 64 else "pih::k_step") + f"<{args.arm}, {args.task}>", "kernel_us": kern_s * 1e6,
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"}},
             "cpu_baseline": cpu,
