@@ -415,3 +415,24 @@ def test_classic_and_warp_specialised_kernels_agree(arm, task, monkeypatch):
     assert torch.equal(sims["0"].state, sims["1"].state)
     assert torch.equal(sims["0"].obs, sims["1"].obs) and torch.equal(sims["0"].done, sims["1"].done)
     _assert_state_equal(sims["1"], orc)
+
+
+@pytest.mark.parametrize("n,arm,task,fly,dt", [(16384, "ur5", "peg-in-hole", "banana", 1.0 / 240.0),      # BASELINE config 3
+                                                (65536, "panda", "random-fly", "banana", 1.0 / 120.0)])    # BASELINE config 4
+def test_full_size_properties_other_configs(n, arm, task, fly, dt):
+    """Full BASELINE sizes of configs 3 and 4 (classic kernels): determinism, split-rollout equivalence, invariants,
+    and an oracle spot check on a slice of the envs."""
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    kw = dict(arm=arm, task=task, fly_object=fly, dt=dt, offset=(2.0, 3.0, 0.0), seed=77, max_steps=60, auto_reset=True)
+    a = BatchedSim(n, device=0, **kw); a.reset(); a.rollout(90)
+    b = BatchedSim(n, device=0, **kw); b.reset(); b.rollout(40); b.rollout(50)
+    assert torch.equal(a.state, b.state)
+    st = a.state.cpu().numpy()
+    assert np.isfinite(st).all()
+    assert np.allclose(np.linalg.norm(ol.state_field(st, ol.S_PQUAT, 4), axis=1), 1.0, atol=1e-5)
+    assert (ol.state_int(st, 10) >= 1).all() and int(a.counters[0].item()) == n * 90
+    m = 96                                                   # oracle on the first 96 envs (same global ids)
+    orc = ol.Oracle(ol.make_config(m, sub_num=n, arm={"panda": 0, "ur5": 1}[arm], task={"peg-in-hole": 0, "random-fly": 1}[task],
+                                   dt=dt, offset=(2.0, 3.0, 0.0), seed=77, max_steps=60, auto_reset=1))
+    orc.reset(); orc.rollout(90)
+    assert np.array_equal(st[:, :m], orc.get_state())
