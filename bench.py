@@ -266,15 +266,18 @@ def main():
     barrier()
     roll_ms = e0.elapsed_time(e1)
     # e2e: host buffers through pih_step_host
-    h_ring = [acts[b % nb_batches][b % n_act].cpu().numpy() for b in range(8)]
-    obs_h, rew_h, done_h = np.zeros((n, 5), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    # e2e: the host-buffer plugin call (pih_step_host) with page-locked host buffers: every step copies that step's actions
+    # H2D, runs the step, and reads (obs, reward, done) back D2H before returning
+    h_acts, obs_h, rew_h, done_h = sim.pinned_host_buffers(8)
+    for b in range(8):
+        h_acts[b][...] = acts[b % nb_batches][b % n_act].cpu().numpy()
     e2e_steps = min(args.steps, 400)
     for i in range(5):
-        sim.step_host(h_ring[i % 8], obs_h, rew_h, done_h)
+        sim.step_host(h_acts[i % 8], obs_h, rew_h, done_h)
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        sim.step_host(h_ring[i % 8], obs_h, rew_h, done_h)
+        sim.step_host(h_acts[i % 8], obs_h, rew_h, done_h)
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -314,7 +317,7 @@ def main():
                               if args.l2 == "rotate" else "flushed between timed steps (256 MiB memset); per-step CUDA events summed"),
                        "gather_to_rank0": bool(args.gather), "parallelism": f"env-sharded x{world}, no data-path collective"},
             "e2e": {"value": total_envs * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * adim * 4,
-                    "d2h_bytes_per_step": n * (20 + 4 + 1), "steps": e2e_steps, "timing": "wall clock incl. pinned staging + H2D + step + D2H + sync"},
+                    "d2h_bytes_per_step": n * (20 + 4 + 1), "steps": e2e_steps, "timing": "wall clock: H2D from pinned host actions + step + one D2H of obs|reward|done into pinned host memory + stream sync, every step"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (ach_tf / peak_tf) if peak_tf else None, "traffic": NCU_TRAFFIC_BYTES if (args.arm == "panda" and n == ENVS_PER_GPU) else None,

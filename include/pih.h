@@ -77,8 +77,10 @@ int pih_reset(pih_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stre
  * previous outputs (base_env.py:61-71) unless auto_reset. */
 int pih_step(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream);
 
-/* Same call with HOST buffers: the reference-facing plugin path (host lists in, host lists out).  Stages through
- * pinned memory, H2D, step, D2H, and synchronises the stream before returning. */
+/* Same call with HOST buffers: the reference-facing plugin path (host lists in, host lists out): H2D, step, D2H,
+ * stream synchronised before returning.  Pageable buffers are staged through the handle's pinned block; page-locked
+ * caller buffers are used for the DMA directly (results in ONE copy when obs/reward/done are one pinned block laid
+ * out [obs n*5 f32 | reward n f32 | done n u8]). */
 int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host, void* stream);
 
 /* Benchmark / synthetic rollouts: `steps` consecutive env.steps in ONE launch with actions

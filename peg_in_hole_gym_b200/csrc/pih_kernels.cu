@@ -533,6 +533,12 @@ static int ensure_staging(pih_handle* h) {
   return PIH_OK;
 }
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host, void* stream) {
   if (!h || !action_host) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "step() before reset()", cudaSuccess);
@@ -540,17 +546,24 @@ int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, floa
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   size_t n = (size_t)h->P.n, A = (size_t)pih_action_dim(h->P.arm);
-  memcpy(h->h_action, action_host, n * A * sizeof(float));
-  cudaError_t ce = cudaMemcpyAsync(h->d_action, h->h_action, n * A * sizeof(float), cudaMemcpyHostToDevice, st);
+  // page-locked caller buffers are used for the DMA directly; pageable ones go through the pinned staging block
+  const float* src = action_host;
+  if (!is_pinned(action_host)) { memcpy(h->h_action, action_host, n * A * sizeof(float)); src = h->h_action; }
+  cudaError_t ce = cudaMemcpyAsync(h->d_action, src, n * A * sizeof(float), cudaMemcpyHostToDevice, st);
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "H2D", ce);
   rc = pih_step(h, h->d_action, h->d_obs, h->d_reward, h->d_done, stream);
   if (rc) return rc;
-  ce = cudaMemcpyAsync(h->h_obs, h->d_obs, out_bytes(n), cudaMemcpyDeviceToHost, st);
+  // one D2H straight into the caller's memory when it is one pinned block laid out [obs | reward | done]
+  const bool direct = obs_host && reward_host && done_host && reward_host == obs_host + n * 5 &&
+                      done_host == reinterpret_cast<uint8_t*>(reward_host + n) && is_pinned(obs_host);
+  ce = cudaMemcpyAsync(direct ? obs_host : h->h_obs, h->d_obs, out_bytes(n), cudaMemcpyDeviceToHost, st);
   if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "D2H", ce);
-  if (obs_host) memcpy(obs_host, h->h_obs, n * 5 * sizeof(float));
-  if (reward_host) memcpy(reward_host, h->h_reward, n * sizeof(float));
-  if (done_host) memcpy(done_host, h->h_done, n);
+  if (!direct) {
+    if (obs_host) memcpy(obs_host, h->h_obs, n * 5 * sizeof(float));
+    if (reward_host) memcpy(reward_host, h->h_reward, n * sizeof(float));
+    if (done_host) memcpy(done_host, h->h_done, n);
+  }
   return PIH_OK;
 }
 

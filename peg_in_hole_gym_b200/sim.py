@@ -85,6 +85,21 @@ class BatchedSim:
         N.check(self._L.pih_step_host(self._h, action_np.ctypes.data, obs_np.ctypes.data, reward_np.ctypes.data,
                                       done_np.ctypes.data, self._stream()), self._h, "pih_step_host")
 
+    def pinned_host_buffers(self, n_action_buffers=1):
+        """Page-locked numpy views for the host-buffer call: `n_action_buffers` action arrays [N, A] and ONE block laid
+        out [obs | reward | done] so that the results come back in a single DMA without staging copies."""
+        import numpy as np
+        acts = [torch.empty(self.n, self.action_dim, dtype=torch.float32).pin_memory() for _ in range(n_action_buffers)]
+        nbytes = self.n * (self.obs_dim * 4 + 4 + 1)
+        self._pinned_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        self._pinned_act = acts
+        raw = self._pinned_out.numpy()
+        o_end, r_end = self.n * self.obs_dim * 4, self.n * self.obs_dim * 4 + self.n * 4
+        obs = raw[:o_end].view(np.float32).reshape(self.n, self.obs_dim)
+        rew = raw[o_end:r_end].view(np.float32)
+        done = raw[r_end:]
+        return [a.numpy() for a in acts], obs, rew, done
+
     def rollout(self, steps, count=True):
         """`steps` env.steps in one launch with in-kernel U[-1,1] actions (action_space.sample(), README.md:48)."""
         N.check(self._L.pih_rollout(self._h, int(steps), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),

@@ -208,6 +208,14 @@ def test_step_host_path_equals_device_path():
         sim_b.step_host(a, obs, rew, done)
     assert np.array_equal(sim_a.obs.cpu().numpy(), obs)
     assert np.array_equal(sim_a.state.cpu().numpy(), sim_b.state.cpu().numpy())
+    # page-locked caller buffers: DMA straight from / into the caller's memory (one D2H for obs|reward|done)
+    (pa,), pobs, prew, pdone = sim_b.pinned_host_buffers(1)
+    for a in acts[:5]:
+        sim_a.step(torch.from_numpy(a).cuda())
+        pa[...] = a
+        sim_b.step_host(pa, pobs, prew, pdone)
+    assert np.array_equal(sim_a.obs.cpu().numpy(), pobs) and np.array_equal(sim_a.reward.cpu().numpy(), prew)
+    assert np.array_equal(sim_a.done.cpu().numpy(), pdone)
 
 
 def test_fp32_gpu_vs_fp64_oracle_drift_within_tolerance():

@@ -217,3 +217,30 @@ def test_camera_render_sees_table_and_peg():
     assert abs(z_table - (ee_z + 0.05)) < 2e-3               # corner pixel sees the table at z = -0.05
     assert (rgb[0, 30, 30] > rgb[0, 0, 0]).all()             # peg (white) in the image centre, table (brown) at the corner
     assert np.array_equal(rgb, np.round(rgb)) and rgb.min() >= 0 and rgb.max() <= 255
+
+
+def test_ur5_holds_its_pose_and_fly_object_is_ballistic():
+    """ur5: POSITION_CONTROL kp 0.03 / 300 N m (utils.py:82) holds the arm against gravity when the target is the
+    current pose; random-fly: before any contact the thrown object follows the semi-implicit-Euler parabola."""
+    from scipy.spatial.transform import Rotation as Rot
+    o = ol.Oracle(ol.make_config(1, arm=1, seed=1), use_double=True)
+    o.reset()
+    q0 = ol.state_field(o.get_state(), ol.S_Q, 9)[0, :6].astype(np.float64)
+    p, R = ol.fk(1, q0, True)
+    eul = Rot.from_matrix(R).as_euler("xyz")                 # getQuaternionFromEuler: fixed-axis XYZ
+    a = np.array([[p[0], p[1], p[2], eul[0], eul[1], eul[2]]], np.float32)
+    for _ in range(240):
+        o.step(a)
+    assert np.abs(ol.state_field(o.get_state(), ol.S_Q, 9)[0, :6] - q0).max() < 1e-4
+    o = ol.Oracle(ol.make_config(4, task=1, dt=1.0 / 120.0, seed=2, offset=(2.0, 0.0, 0.0)), use_double=True)
+    o.reset()
+    w0 = o.get_state()
+    p0, v0 = ol.state_field(w0, ol.S_PPOS, 3).astype(np.float64), ol.state_field(w0, ol.S_PVEL, 3).astype(np.float64)
+    act = np.zeros((4, 4), np.float32)
+    act[:, :3] = o.obs[:, 2:5]
+    k, dt = 20, 1.0 / 120.0
+    for _ in range(k):
+        o.step(act)
+    want = p0 + v0 * dt * k
+    want[:, 2] -= 9.8 * dt * dt * k * (k + 1) / 2
+    assert np.abs(ol.state_field(o.get_state(), ol.S_PPOS, 3) - want).max() < 1e-6
