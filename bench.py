@@ -64,7 +64,7 @@ class ClockSampler:
         self.rows, self.p = [], None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                       "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.p = None
@@ -147,8 +147,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=4000)
+    ap.add_argument("--warmup", type=int, default=400)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--arm", default="panda")
@@ -271,7 +271,7 @@ def main():
     h_acts, obs_h, rew_h, done_h = sim.pinned_host_buffers(8)
     for b in range(8):
         h_acts[b][...] = acts[b % nb_batches][b % n_act].cpu().numpy()
-    e2e_steps = min(args.steps, 400)
+    e2e_steps = min(args.steps, 2000)
     for i in range(5):
         sim.step_host(h_acts[i % 8], obs_h, rew_h, done_h)
     barrier()
