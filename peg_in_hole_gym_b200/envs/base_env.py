@@ -21,20 +21,28 @@ TASK_LIST = {
 
 
 class LazyInfos:
-    """`infos` of the reference is a list of dicts (base_env.py:90); materialising N dicts per step would cap
-    throughput, so dicts are built on access.  Indexes like the nested lists."""
+    """`infos` of the reference is a list of dicts (base_env.py:90); materialising N dicts (or even reading the flags
+    word back) per step would cap throughput, so nothing is computed until an element is
+    accessed: then the flags word of the state is read once and dicts are built on demand.  Indexes like the
+    reference's nested lists."""
 
-    def __init__(self, shape, flags):
-        self._shape, self._flags = tuple(shape), flags
+    def __init__(self, shape, sim=None, flags=None):
+        self._shape, self._sim, self._flags = tuple(shape), sim, flags
+
+    def _load(self):
+        if self._flags is None:
+            self._flags = self._sim.int_word(11).cpu().numpy()
+        return self._flags
 
     def __len__(self):
         return self._shape[0]
 
     def __getitem__(self, i):
+        flags = self._load()
         if len(self._shape) > 1:
             n = int(np.prod(self._shape[1:]))
-            return LazyInfos(self._shape[1:], self._flags[i * n:(i + 1) * n])
-        f = int(self._flags[i])
+            return LazyInfos(self._shape[1:], flags=flags[i * n:(i + 1) * n])
+        f = int(flags[i])
         return {"success": bool(f & 2), "contact_pairs": (f >> 8) & 0xff}
 
     def tolist(self):
@@ -89,7 +97,7 @@ class BaseEnv(gym.Env):
     def _pack(self, obs, reward, done):
         shp = self._shape()
         obs, reward, done = obs.view(*shp, -1), reward.view(*shp), done.view(*shp).bool()
-        infos = LazyInfos(shp, self.sim.int_word(11))
+        infos = LazyInfos(shp, sim=self.sim)
         if self.as_lists:
             return obs.cpu().numpy().tolist(), reward.cpu().numpy().tolist(), done.cpu().numpy().tolist(), infos.tolist()
         return obs, reward, done, infos
