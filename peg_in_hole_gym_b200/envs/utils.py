@@ -16,9 +16,9 @@ def test_mode(test_key, func):
 
 
 def data_normalize(data, normalize_range):
-    """envs/utils.py:19-22 - in-place (x-lo)/(hi-lo) per component."""
-    for i in range(len(data)):
-        data[i] = (data[i] - normalize_range[i][0]) / (normalize_range[i][1] - normalize_range[i][0])
+    """envs/utils.py:19-22 - in-place (x - lo) / (hi - lo) per component; returns the same object."""
+    for i, (lo, hi) in enumerate(normalize_range[:len(data)]):
+        data[i] = (data[i] - lo) / (hi - lo)
     return data
 
 
@@ -74,95 +74,76 @@ def ur_execute(client, ur_id, action, urEndEffectorIndex=7, urNumDofs=6, dv=2 / 
 
 
 def vel_constraint(cur, tar, dv):
-    """envs/utils.py:85-95 - per-axis clamp of the step toward an absolute target."""
-    res = []
-    for i in range(len(tar)):
-        diff = tar[i] - cur[i]
-        if abs(diff) > dv:
-            re = cur[i] + (dv if diff > 0 else -dv)
-        else:
-            re = cur[i] + diff
-        res.append(re)
-    return res
+    """envs/utils.py:85-95 - move from `cur` toward the absolute target `tar`, at most `dv` per axis."""
+    return [c + max(-dv, min(dv, t - c)) for c, t in zip(cur, tar)]
 
 
 def random_pos_in_panda_space():
-    """envs/utils.py:97-107 - rejection-sample a point of the radius-0.7 sphere cap above the panda."""
-    x = y = z = 1
-    length = 0.7
-    while (length * length - x * x - y * y) < 0:
-        x = random.uniform(-length, length)
-        y = (math.sqrt(random.uniform(0, length * length - x * x)) - random.uniform(0, 0.4)) * random.choice([-1, 1])
-    z = math.sqrt(length * length - x * x - y * y) + 0.2
-    return np.array([x, y, z])
+    """envs/utils.py:97-107 - point on the radius-0.7 sphere centred (0, 0, 0.2), above the panda: x uniform,
+    |y| = sqrt(U(0, r^2 - x^2)) - U(0, 0.4) with a random sign, resampled until it lies inside the disc."""
+    radius = 0.7
+    r2 = radius * radius
+    while True:
+        x = random.uniform(-radius, radius)
+        y = (math.sqrt(random.uniform(0, r2 - x * x)) - random.uniform(0, 0.4)) * random.choice([-1, 1])
+        rest = r2 - x * x - y * y
+        if rest >= 0:
+            return np.array([x, y, math.sqrt(rest) + 0.2])
 
 
-class MultiAgentObservationSpace(list):
+class _AgentSpaces(list):
+    """Common part of the four containers of envs/utils.py:132-209: a list of per-agent spaces that also exposes
+    `.shape/.high/.low` of the first child and samples every child.  `_as_list=False` reproduces the reference's MP
+    variants, which skip list.__init__ and therefore have len() == 0."""
+    _child_type = spaces.space.Space
+    _as_list = True
+
+    def __init__(self, children):
+        children = list(children)
+        assert all(isinstance(c, self._child_type) for c in children)
+        if self._as_list:
+            super().__init__(children)
+        self._children = children
+        first = children[0]
+        self.shape, self.high, self.low = first.shape, first.high, first.low
+
+    def sample(self):
+        return [c.sample() for c in self._children]
+
+    def contains(self, items):
+        return all(c.contains(x) for c, x in zip(self._children, items))
+
+
+class MultiAgentObservationSpace(_AgentSpaces):
     """envs/utils.py:132-153."""
 
-    def __init__(self, agents_observation_space):
-        for x in agents_observation_space:
-            assert isinstance(x, spaces.space.Space)
-        super().__init__(agents_observation_space)
-        self._agents_observation_space = agents_observation_space
-        self.shape = agents_observation_space[0].shape
-        self.high = agents_observation_space[0].high
-        self.low = agents_observation_space[0].low
-
-    def sample(self):
-        return [s.sample() for s in self._agents_observation_space]
-
-    def contains(self, obs):
-        for space, ob in zip(self._agents_observation_space, obs):
-            if not space.contains(ob):
-                return False
-        return True
+    @property
+    def _agents_observation_space(self):
+        return self._children
 
 
-class MultiAgentActionSpace(list):
-    """envs/utils.py:156-170."""
+class MultiAgentActionSpace(_AgentSpaces):
+    """envs/utils.py:156-170 (+ NEW sample_array: one [sub, A] float32 array instead of `sub` Python objects)."""
 
-    def __init__(self, agents_action_space):
-        for x in agents_action_space:
-            assert isinstance(x, spaces.space.Space)
-        super().__init__(agents_action_space)
-        self._agents_action_space = agents_action_space
-        self.shape = agents_action_space[0].shape
-        self.high = agents_action_space[0].high
-        self.low = agents_action_space[0].low
-
-    def sample(self):
-        return [s.sample() for s in self._agents_action_space]
+    @property
+    def _agents_action_space(self):
+        return self._children
 
     def sample_array(self):
-        """NEW: one [sub, A] float32 array (avoids sub_num Python objects per step)."""
-        s0 = self._agents_action_space[0]
-        return s0._rng.uniform(s0.low, s0.high, (len(self._agents_action_space),) + s0.shape).astype(np.float32)
+        s0 = self._children[0]
+        return s0._rng.uniform(s0.low, s0.high, (len(self._children),) + s0.shape).astype(np.float32)
 
 
 class MPMultiAgentObservationSpace(MultiAgentObservationSpace):
-    """envs/utils.py:173-193 - like the reference it does NOT call list.__init__, so len() == 0 (Appendix A.9)."""
-
-    def __init__(self, agents_observation_space):
-        for x in agents_observation_space:
-            assert isinstance(x, MultiAgentObservationSpace)
-        self._agents_observation_space = agents_observation_space
-        self.shape = agents_observation_space[0].shape
-        self.high = agents_observation_space[0].high
-        self.low = agents_observation_space[0].low
+    """envs/utils.py:173-193."""
+    _child_type = MultiAgentObservationSpace
+    _as_list = False
 
 
 class MPMultiAgentActionSpace(MultiAgentActionSpace):
-    """envs/utils.py:196-209."""
-
-    def __init__(self, agents_action_space):
-        for x in agents_action_space:
-            assert isinstance(x, MultiAgentActionSpace)
-        self._agents_action_space = agents_action_space
-        self.shape = agents_action_space[0].shape
-        self.high = agents_action_space[0].high
-        self.low = agents_action_space[0].low
+    """envs/utils.py:196-209 (+ NEW sample_array: one [mp, sub, A] float32 array)."""
+    _child_type = MultiAgentActionSpace
+    _as_list = False
 
     def sample_array(self):
-        """NEW: one [mp, sub, A] float32 array."""
-        return np.stack([s.sample_array() for s in self._agents_action_space])
+        return np.stack([c.sample_array() for c in self._children])
