@@ -317,6 +317,14 @@ static int fail(pih_handle* h, int code, const char* what, cudaError_t ce) {
   return code;
 }
 
+// make the handle's device current (cheap when it already is): launches must go to the device that owns the state
+static int use_device(pih_handle* h) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) == cudaSuccess && cur == h->cfg.device) return PIH_OK;
+  cudaError_t ce = cudaSetDevice(h->cfg.device);
+  return ce == cudaSuccess ? PIH_OK : fail(h, PIH_ERR_CUDA, "cudaSetDevice", ce);
+}
+
 #define FILL_ARM(T, P)                                                                          \
   do {                                                                                          \
     (T).nb = PIH_##P##_NB; (T).narm = PIH_##P##_NARM; (T).ee_body = PIH_##P##_EE_BODY;            \
@@ -505,6 +513,7 @@ int pih_reset(pih_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stre
 int pih_step(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream) {
   if (!h || !action_dev) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "step() before reset()", cudaSuccess);
+  if (use_device(h)) return PIH_ERR_CUDA;
   if (h->ws) { LAUNCH_WS(k_step_ws, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev); }
   else { LAUNCH(k_step, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev); }
   cudaError_t ce = cudaGetLastError();
@@ -570,6 +579,7 @@ int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, floa
 int pih_rollout(pih_handle* h, int32_t steps, float* obs_dev, float* reward_dev, uint8_t* done_dev, unsigned long long* counters_dev, void* stream) {
   if (!h || steps < 0) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "rollout() before reset()", cudaSuccess);
+  if (use_device(h)) return PIH_ERR_CUDA;
   if (h->ws) { LAUNCH_WS(k_rollout_ws, h, stream, h->P, (int)steps, obs_dev, reward_dev, done_dev, counters_dev); }
   else { LAUNCH(k_rollout, h, stream, h->P, (int)steps, obs_dev, reward_dev, done_dev, counters_dev); }
   cudaError_t ce = cudaGetLastError();
@@ -580,6 +590,7 @@ int pih_rollout(pih_handle* h, int32_t steps, float* obs_dev, float* reward_dev,
 
 int pih_ik_targets(pih_handle* h, const float* action_dev, float* qtarget_dev, void* stream) {
   if (!h || !action_dev || !qtarget_dev) return PIH_ERR_INVALID;
+  if (use_device(h)) return PIH_ERR_CUDA;
   LAUNCH(k_ik, h, stream, h->P, action_dev, qtarget_dev);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_ik launch", ce);
@@ -588,6 +599,7 @@ int pih_ik_targets(pih_handle* h, const float* action_dev, float* qtarget_dev, v
 
 int pih_ee_pose(pih_handle* h, float* pos_dev, float* rot_dev, void* stream) {
   if (!h) return PIH_ERR_INVALID;
+  if (use_device(h)) return PIH_ERR_CUDA;
   LAUNCH_ARM(k_ee, h, stream, h->P, pos_dev, rot_dev);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_ee launch", ce);
@@ -597,6 +609,7 @@ int pih_ee_pose(pih_handle* h, float* pos_dev, float* rot_dev, void* stream) {
 int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, void* stream) {
   if (!h || !rgbd_dev || width <= 0 || height <= 0) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "render() before reset()", cudaSuccess);
+  if (use_device(h)) return PIH_ERR_CUDA;
   if (!h->d_scene) {
     cudaError_t ce = cudaMalloc(&h->d_scene, (size_t)h->P.n * PIH_SCENE_WORDS * sizeof(float));
     if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "scene allocation", ce);
