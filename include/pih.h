@@ -73,14 +73,17 @@ int pih_reset(pih_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stre
 
 /* BaseEnvMp.step -> worker -> BaseEnv.step (base_env_mp.py:40-51,75-87, base_env.py:60-75): apply_action
  * (panda_execute / ur_execute, utils.py:60-82), one stepSimulation, get_info.  action_dev float[num_envs][A];
- * obs_dev float[num_envs][5]; reward_dev float[num_envs]; done_dev uint8[num_envs].  Envs that are done keep their
- * previous outputs (base_env.py:61-71) unless auto_reset. */
+ * obs_dev float[num_envs][5]; reward_dev float[num_envs]; done_dev uint8[num_envs].  Envs that are done are not
+ * stepped and report their last outputs again (base_env.py:61-71) unless auto_reset.  action_dev must be 16-byte
+ * aligned (Box(4) rows are read as one 128-bit word) / 8-byte aligned (Box(6)). */
 int pih_step(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream);
 
-/* Same call with HOST buffers: the reference-facing plugin path (host lists in, host lists out): H2D, step, D2H,
- * stream synchronised before returning.  Pageable buffers are staged through the handle's pinned block; page-locked
- * caller buffers are used for the DMA directly (results in ONE copy when obs/reward/done are one pinned block laid
- * out [obs n*5 f32 | reward n f32 | done n u8]). */
+/* Same call with HOST buffers: the reference-facing plugin path (host lists in, host lists out); the stream is
+ * synchronised before returning.  When all four buffers are page-locked and device-mapped (cudaHostAlloc /
+ * cudaHostRegister, e.g. torch pin_memory) the step kernel reads the actions from and writes the results to host
+ * memory itself: ONE launch, no staging copies (zero-copy over PCIe).  Otherwise pageable buffers are staged through
+ * the handle's pinned block: H2D, step, ONE D2H of [obs n*5 f32 | reward n f32 | done n u8].  Done envs re-emit their
+ * last outputs (they are a function of the frozen state), so the output buffers may be fresh every call. */
 int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host, void* stream);
 
 /* Benchmark / synthetic rollouts: `steps` consecutive env.steps in ONE launch with actions

@@ -1333,13 +1333,17 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
   for (int it = 0; it < C->solver_iters; ++it) {
     real res_a = RC(0), res_f = RC(0);
 #define PIH_RES(acc_, dl_, diag_) do { real rv_ = (dl_) * (diag_); rv_ = rv_ * rv_; if (rv_ > acc_) acc_ = rv_; } while (0)
+    /* Accumulated-impulse projection of one row (btMultiBodyConstraintSolver::resolveSingleConstraintRowGeneric [3P]:
+     * sum = applied + delta, clamped to [lower, upper]).  Stated on the delta: delta is clamped to
+     * [lower - applied, upper - applied] and then accumulated - the same projection, with the shortest dependent chain
+     * (delta -> min/max -> velocity update); applied may sit one rounding off a bound, which the next sweep corrects. */
+#define PIH_PROJECT(dl_, lam_, lo_, hi_) do { real dlo_ = (lo_) - (lam_), dhi_ = (hi_) - (lam_); \
+      dl_ = ((dl_) < dlo_) ? dlo_ : (dl_); dl_ = ((dl_) > dhi_) ? dhi_ : (dl_); lam_ = (lam_) + (dl_); } while (0)
+#define PIH_PROJECT_LO(dl_, lam_) do { real dlo_ = -(lam_); dl_ = ((dl_) < dlo_) ? dlo_ : (dl_); lam_ = (lam_) + (dl_); } while (0)
     if (arm_on) {
       for (int j = 0; j < nb; ++j) {
         real dl = FMA(-dva[j], m_dinv[j], m_b[j]);
-        real s = m_lam[j] + dl;
-        s = (s > m_max[j]) ? m_max[j] : ((s < -m_max[j]) ? -m_max[j] : s);
-        dl = s - m_lam[j];
-        m_lam[j] = s;
+        PIH_PROJECT(dl, m_lam[j], -m_max[j], m_max[j]);
         PIH_RES(res_a, dl, Minv[j][j]);
         for (int i = 0; i < nb; ++i) dva[i] = FMA(Minv[i][j], dl, dva[i]);
       }
@@ -1348,10 +1352,8 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
           if (!l_on[side][j]) continue;
           real sg = side ? RC(-1) : RC(1);
           real dl = FMA(-(sg * dva[j]), m_dinv[j], l_b[side][j]);
-          real s = l_lam[side][j] + dl;
-          s = (s < RC(0)) ? RC(0) : s;
-          dl = (s - l_lam[side][j]) * sg;
-          l_lam[side][j] = s;
+          PIH_PROJECT_LO(dl, l_lam[side][j]);
+          dl = dl * sg;
           PIH_RES(res_a, dl, Minv[j][j]);
           for (int i = 0; i < nb; ++i) dva[i] = FMA(Minv[i][j], dl, dva[i]);
         }
@@ -1370,20 +1372,19 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
             rel = rel + ra;
           }
           real dl = FMA(-rel, r->dinv[d], r->b[d]);
-          real s = r->lam[d] + dl;
-          if (d == 0) s = (s < RC(0)) ? RC(0) : s;
+          if (d == 0) PIH_PROJECT_LO(dl, r->lam[d]);
           else {
             real lim = r->mu * r->lam[0];
-            s = (s > lim) ? lim : ((s < -lim) ? -lim : s);
+            PIH_PROJECT(dl, r->lam[d], -lim, lim);
           }
-          dl = s - r->lam[d];
-          r->lam[d] = s;
           if (is_fb) PIH_RES(res_f, dl, r->diag[d]); else PIH_RES(res_a, dl, r->diag[d]);
           if (r->has_fb) { dvl = FN(v3_axpy)(dl * im, r->dir[d], dvl); dvw = FN(v3_axpy)(dl, r->mang[d], dvw); }
           if (r->arm_body >= 0) for (int j = 0; j < nb; ++j) dva[j] = FMA(r->ma[d][j], dl, dva[j]);
         }
       }
 #undef PIH_RES
+#undef PIH_PROJECT
+#undef PIH_PROJECT_LO
     pih_dbg_pgs_iters += 1;
     if (coupled) {
       if (((res_a > res_f) ? res_a : res_f) <= C->solver_residual) break;

@@ -1,6 +1,7 @@
 // pih_kernels.cu - kernels + C ABI (include/pih.h) of the B200-native batched peg-in-hole simulator.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -Xcompiler -fPIC -shared
 // There is NO CPU fallback in this library: every entry point drives a CUDA kernel or fails with PIH_ERR_CUDA.
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -36,6 +37,29 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128) k_reset(SimP
   }
 }
 
+// A done env is not stepped and keeps its last outputs (base_env.py:61-71).  Those outputs are a function of the frozen
+// state (observation of the post-step state, reward = success flag, done = 1), so they are re-emitted from it: the
+// caller may hand in fresh output buffers every step (the zero-copy host path does).
+template <int ARM> PIH_D void frozen_outputs(const EnvState& S, v3 off, float (&o)[5], float& r, unsigned char& d) {
+  observe<ARM>(S, off, o);
+  r = (S.flags & PIH_FLAG_SUCCESS) ? 1.0f : 0.0f;
+  d = 1;
+}
+
+// one env's action row: a single 128-bit load for Box(4), three 64-bit loads for Box(6) (rows are 16 B / 24 B apart)
+template <int A> PIH_D void load_action(const float* __restrict__ action, int e, float (&a)[6]) {
+  if (A == 4) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(action) + e);
+    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; a[4] = 0.0f; a[5] = 0.0f;
+  } else {
+#pragma unroll
+    for (int k = 0; k < A / 2; ++k) {
+      float2 v = __ldg(reinterpret_cast<const float2*>(action) + (size_t)(A / 2) * e + k);
+      a[2 * k] = v.x; a[2 * k + 1] = v.y;
+    }
+  }
+}
+
 template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOCKS) k_step(SimParams P, const float* __restrict__ action, float* __restrict__ obs,
                                                                 float* __restrict__ reward, unsigned char* __restrict__ done) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -43,18 +67,12 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOC
   constexpr int A = ArmDims<ARM>::ADIM;
   EnvState S;
   load_state(P, e, S);
-  float a[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-  if (A == 4) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(action) + e);
-    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-  } else {
-#pragma unroll
-    for (int k = 0; k < A; ++k) a[k] = __ldg(&action[(size_t)A * e + k]);
-  }
+  float a[6];
+  load_action<A>(action, e, a);
   float o[5], r;
   unsigned char d;
-  if (!step_env<ARM, TASK>(P, S, a, env_offset(P, e), (unsigned)(P.env_id_base + e), o, r, d)) return;  // frozen: keep outputs
-  store_state(P, e, S);
+  if (step_env<ARM, TASK>(P, S, a, env_offset(P, e), (unsigned)(P.env_id_base + e), o, r, d)) store_state(P, e, S);
+  else frozen_outputs<ARM>(S, env_offset(P, e), o, r, d);
   if (obs) {
 #pragma unroll
     for (int k = 0; k < 5; ++k) obs[5 * (size_t)e + k] = o[k];
@@ -145,9 +163,8 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(
   fk<ARM, nb>(S.q, F);
   float qs[nb], kpc[nb], mfc[nb];
   if (w == 0) {
-    float a[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-    for (int k = 0; k < A; ++k) a[k] = __ldg(&action[(size_t)A * ec + k]);
+    float a[6];
+    load_action<A>(action, ec, a);
     const bool fd = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc);
     mailbox_put<ARM, TASK>(mb, lane, qs, kpc, mfc, fd, S);
     __syncthreads();
@@ -156,12 +173,24 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(
   float o[5], r;
   unsigned char d;
   step_back_ws<ARM, TASK>(P, S, F, qs, kpc, mfc, false, mb, lane, active, off, (unsigned)(P.env_id_base + ec), o, r, d);
-  if (!active) return;
-  store_state(P, e, S);
+  if (active) store_state(P, e, S);
+  else frozen_outputs<ARM>(S, off, o, r, d);   // done env (or a padding lane, which writes nothing below)
   if (obs) {
+    // the CTA's 32 observation rows are 640 contiguous bytes: transpose through the (now idle) mailbox so that the
+    // warp writes five full 128-byte lines instead of 160 scattered words (matters when obs is mapped host memory)
+    float* so = &mb[0][0];
+    __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 5; ++k) obs[5 * (size_t)e + k] = o[k];
+    for (int k = 0; k < 5; ++k) so[5 * lane + k] = o[k];
+    __syncwarp();
+    const int rows = min(32, P.n - (int)blockIdx.x * 32);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int idx = 32 * k + lane;
+      if (idx < 5 * rows) obs[(size_t)blockIdx.x * 160 + idx] = so[idx];
+    }
   }
+  if (e >= P.n) return;
   if (reward) reward[e] = r;
   if (done) done[e] = d;
 }
@@ -238,9 +267,8 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128) k_ik(SimPara
   constexpr int A = ArmDims<ARM>::ADIM, nb = ArmDims<ARM>::NB;
   EnvState S;
   load_state(P, e, S);
-  float a[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-  for (int k = 0; k < A; ++k) a[k] = action[(size_t)A * e + k];
+  float a[6];
+  load_action<A>(action, e, a);
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
   float qs[nb], kpc[nb], mfc[nb];
@@ -295,6 +323,7 @@ __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a
 // ------------------------------------------------------------------------------------------------ host side
 using namespace pih;
 
+#define PIH_ALIAS_SLOTS 96
 struct pih_handle {
   pih_config cfg;
   SimParams P;
@@ -308,6 +337,10 @@ struct pih_handle {
   float *d_action, *d_obs, *d_reward;
   unsigned char* d_done;
   float* d_scene;  // render pre-pass output [n][PIH_SCENE_WORDS], allocated on first pih_render
+  // host pointer -> mapped device alias cache of pih_step_host
+  const void* alias_host[PIH_ALIAS_SLOTS];
+  void* alias_dev[PIH_ALIAS_SLOTS];
+  int n_alias, alias_next, no_zero_copy;
 };
 
 static int g_tables_device = -1;
@@ -447,6 +480,8 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   h->ws = (P.n <= 148 * 32 * 2) ? 1 : 0;   // up to two 64-thread CTAs per SM: every warp still has a scheduler to itself
   const char* wse = getenv("PIH_WS");
   if (wse) h->ws = atoi(wse) ? 1 : 0;
+  const char* nz = getenv("PIH_NO_ZERO_COPY");   // diagnostics: force the staged-copy host path
+  if (nz) h->no_zero_copy = atoi(nz) ? 1 : 0;
   const char* bs = getenv("PIH_BLOCK");
   if (bs) { int b = atoi(bs); if (b == 32 || b == 64 || b == 128) h->block = b; }
   k_init_state<<<(P.n + 127) / 128, 128>>>(P.state, P.n);
@@ -513,6 +548,7 @@ int pih_reset(pih_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stre
 int pih_step(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream) {
   if (!h || !action_dev) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "step() before reset()", cudaSuccess);
+  if ((uintptr_t)action_dev & (h->P.arm == PIH_ARM_PANDA ? 15 : 7)) return fail(h, PIH_ERR_INVALID, "action rows must be 16-byte (Box(4)) / 8-byte (Box(6)) aligned", cudaSuccess);
   if (use_device(h)) return PIH_ERR_CUDA;
   if (h->ws) { LAUNCH_WS(k_step_ws, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev); }
   else { LAUNCH(k_step, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev); }
@@ -548,13 +584,44 @@ static bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+// Device alias of a page-locked, device-mapped host buffer (NULL when the buffer is pageable or not mapped).  The
+// answer per host pointer is remembered in a small table: callers cycle through a handful of buffers.
+static void* mapped_alias(pih_handle* h, const void* p) {
+  if (!p) return nullptr;
+  for (int i = 0; i < h->n_alias; ++i)
+    if (h->alias_host[i] == p) return h->alias_dev[i];
+  void* d = nullptr;
+  if (is_pinned(p)) {
+    if (cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) { cudaGetLastError(); d = nullptr; }
+  }
+  const int slot = h->n_alias < PIH_ALIAS_SLOTS ? h->n_alias++ : (h->alias_next++ % PIH_ALIAS_SLOTS);
+  h->alias_host[slot] = p; h->alias_dev[slot] = d;
+  return d;
+}
+
 int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host, void* stream) {
   if (!h || !action_host) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "step() before reset()", cudaSuccess);
-  int rc = ensure_staging(h);
-  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   size_t n = (size_t)h->P.n, A = (size_t)pih_action_dim(h->P.arm);
+  // Zero-copy: when every caller buffer is page-locked and device-mapped, the step kernel reads the actions from and
+  // writes (obs, reward, done) to host memory itself (PCIe reads/writes issued by the SMs: 16 B in and 25 B out per
+  // env), so the call is ONE launch plus one stream synchronisation - no staging copies and no copy-engine latency.
+  if (!h->no_zero_copy && obs_host && reward_host && done_host) {
+    float* da = (float*)mapped_alias(h, action_host);
+    float* dob = (float*)mapped_alias(h, obs_host);
+    float* dr = (float*)mapped_alias(h, reward_host);
+    uint8_t* dd = (uint8_t*)mapped_alias(h, done_host);
+    if (da && dob && dr && dd && ((uintptr_t)da & 15) == 0 && ((uintptr_t)dob & 15) == 0) {
+      int rc = pih_step(h, da, dob, dr, dd, stream);
+      if (rc) return rc;
+      cudaError_t ce = cudaStreamSynchronize(st);
+      if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "step (zero-copy) sync", ce);
+      return PIH_OK;
+    }
+  }
+  int rc = ensure_staging(h);
+  if (rc) return rc;
   // page-locked caller buffers are used for the DMA directly; pageable ones go through the pinned staging block
   const float* src = action_host;
   if (!is_pinned(action_host)) { memcpy(h->h_action, action_host, n * A * sizeof(float)); src = h->h_action; }

@@ -82,8 +82,25 @@ class BatchedSim:
 
     def step_host(self, action_np, obs_np, reward_np, done_np):
         """Host-buffer plugin call (pih_step_host): numpy in, numpy out, H2D/D2H inside."""
-        N.check(self._L.pih_step_host(self._h, action_np.ctypes.data, obs_np.ctypes.data, reward_np.ctypes.data,
-                                      done_np.ctypes.data, self._stream()), self._h, "pih_step_host")
+        rc = self._L.pih_step_host(self._h, action_np.ctypes.data, obs_np.ctypes.data, reward_np.ctypes.data,
+                                   done_np.ctypes.data, self._stream())
+        if rc:
+            N.check(rc, self._h, "pih_step_host")
+
+    def host_stepper(self, action_nps, obs_np, reward_np, done_np):
+        """Binds pih_step_host to fixed host buffers once (addresses resolved up front) and returns ``step(i)`` which
+        steps with ``action_nps[i]``: the per-call Python work is one ctypes call.  With page-locked buffers
+        (``pinned_host_buffers``) the library runs its zero-copy path."""
+        a_ptrs = [C.c_void_p(a.ctypes.data) for a in action_nps]
+        o, r, d = C.c_void_p(obs_np.ctypes.data), C.c_void_p(reward_np.ctypes.data), C.c_void_p(done_np.ctypes.data)
+        fn, h, st = self._L.pih_step_host, self._h, C.c_void_p(self._stream())
+        keep = (action_nps, obs_np, reward_np, done_np)
+
+        def step(i, _keep=keep):
+            rc = fn(h, a_ptrs[i], o, r, d, st)
+            if rc:
+                N.check(rc, h, "pih_step_host")
+        return step
 
     def pinned_host_buffers(self, n_action_buffers=1):
         """Page-locked numpy views for the host-buffer call: `n_action_buffers` action arrays [N, A] and ONE block laid

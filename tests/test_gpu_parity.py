@@ -218,6 +218,27 @@ def test_step_host_path_equals_device_path():
     assert np.array_equal(sim_a.done.cpu().numpy(), pdone)
 
 
+@pytest.mark.parametrize("ws", ["0", "1"])
+def test_zero_copy_host_path_with_frozen_envs_and_fresh_buffers(monkeypatch, ws):
+    """pih_step_host on page-locked buffers lets the kernel read actions from / write results to host memory.  Done
+    envs are frozen (base_env.py:61-71): their outputs are re-emitted from the frozen state, so handing in FRESH output
+    buffers every step still returns the last outputs.  Checked against the oracle for both kernel families."""
+    monkeypatch.setenv("PIH_WS", ws)
+    n = 100
+    sim, orc = _pair(n, offset=(2.0, 3.0, 0.0), seed=21, max_steps=6, auto_reset=False)
+    sim.reset(); orc.reset()
+    acts = _random_actions(n, 4, 12, sim.env_offsets().numpy(), 5)
+    for t, a in enumerate(acts):
+        (pa,), pobs, prew, pdone = sim.pinned_host_buffers(1)        # fresh page-locked buffers every step
+        pobs[...] = -7.0; prew[...] = -7.0; pdone[...] = 9
+        pa[...] = a
+        sim.step_host(pa, pobs, prew, pdone)
+        oc, rc, dc = orc.step(a)
+        assert np.array_equal(pobs, oc) and np.array_equal(prew, rc) and np.array_equal(pdone, dc), t
+    assert pdone.all()
+    _assert_state_equal(sim, orc)
+
+
 def test_fp32_gpu_vs_fp64_oracle_drift_within_tolerance():
     """north_star tolerance: <=1e-3 m / 1e-2 rad per step; drift over the 200-step horizon is reported."""
     n = 128
