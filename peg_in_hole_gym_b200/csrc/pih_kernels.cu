@@ -159,6 +159,7 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(
   load_state(P, ec, S);
   const bool active = (e < P.n) && !(S.flags & PIH_FLAG_DONE);
   const v3 off = env_offset(P, ec);
+  PIH_TICK(w == 0 ? 0 : 2);
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
   float qs[nb], kpc[nb], mfc[nb];
@@ -167,12 +168,14 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(
     load_action<A>(action, ec, a);
     const bool fd = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc);
     mailbox_put<ARM, TASK>(mb, lane, qs, kpc, mfc, fd, S);
+    PIH_TICK(1);
     __syncthreads();
     return;
   }
   float o[5], r;
   unsigned char d;
   step_back_ws<ARM, TASK>(P, S, F, qs, kpc, mfc, false, mb, lane, active, off, (unsigned)(P.env_id_base + ec), o, r, d);
+  PIH_TICK(7);
   if (active) store_state(P, e, S);
   else frozen_outputs<ARM>(S, off, o, r, d);   // done env (or a padding lane, which writes nothing below)
   if (obs) {
@@ -504,6 +507,19 @@ void pih_destroy(pih_handle* h) {
 
 const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null handle"; }
 
+#ifdef PIH_FAST_BUILD   // experiment builds (tools/): only the <panda, peg-in-hole> instantiations, a 6x shorter compile
+#define LAUNCH_T(kern, ARMV, h, st, ...) kern<PIH_ARM_PANDA, PIH_TASK_PEG_IN_HOLE><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__)
+#define LAUNCH(kern, h, st, ...)                                                  \
+  do {                                                                            \
+    int grid_ = ((h)->P.n + (h)->block - 1) / (h)->block;                         \
+    LAUNCH_T(kern, PIH_ARM_PANDA, h, st, __VA_ARGS__);                            \
+  } while (0)
+#define LAUNCH_WS(kern, h, st, ...)                                               \
+  do {                                                                            \
+    int gridw_ = ((h)->P.n + 31) / 32;                                            \
+    kern<PIH_ARM_PANDA, PIH_TASK_PEG_IN_HOLE><<<gridw_, 64, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
+  } while (0)
+#else
 #define LAUNCH_T(kern, ARMV, h, st, ...)                                                                                \
   do {                                                                                                                 \
     if ((h)->P.task == PIH_TASK_PEG_IN_HOLE) kern<ARMV, PIH_TASK_PEG_IN_HOLE><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
@@ -528,6 +544,7 @@ const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null hand
     if ((h)->P.arm == PIH_ARM_PANDA) LAUNCH_WS_T(kern, PIH_ARM_PANDA, h, st, __VA_ARGS__); \
     else LAUNCH_WS_T(kern, PIH_ARM_UR5, h, st, __VA_ARGS__);                      \
   } while (0)
+#endif
 #define LAUNCH_ARM(kern, h, st, ...)                                              \
   do {                                                                            \
     int grid_ = ((h)->P.n + (h)->block - 1) / (h)->block;                         \
@@ -698,6 +715,13 @@ int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, vo
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_render launch", ce);
   return PIH_OK;
 }
+
+#ifdef PIH_PHASE_TICKS
+// experiment builds only: SM clock values recorded by CTA 0 at the phase boundaries of the last step kernel
+int pih_debug_ticks(long long* out16) {
+  return cudaMemcpyFromSymbol(out16, g_ticks, 16 * sizeof(long long)) == cudaSuccess ? PIH_OK : PIH_ERR_CUDA;
+}
+#endif
 
 int pih_measure_fp32_peak(int device, double* tflops_out) {
   if (!tflops_out) return PIH_ERR_INVALID;

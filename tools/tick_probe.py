@@ -1,0 +1,54 @@
+#!/usr/bin/env python3
+"""Phase timing of the warp-specialised step kernel in a HOT run (dev tool; needs an experiment build:
+tools/fast_build.sh ticks -DPIH_PHASE_TICKS, then PIH_LIB=tools/_build/libpih_ticks.so python tools/tick_probe.py).
+CTA 0 records the SM clock at the phase boundaries; medians over many steps, in microseconds at 1965 MHz."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from peg_in_hole_gym_b200 import _native  # noqa: E402
+from peg_in_hole_gym_b200.sim import BatchedSim  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 400
+L = _native.lib()
+sim = BatchedSim(n, offset=(2.0, 3.0, 0.0), max_steps=200, auto_reset=True, seed=0, device=0)
+sim.reset()
+offs = sim.env_offsets().cuda()
+g = torch.Generator(device="cuda"); g.manual_seed(1)
+acts = []
+for _ in range(64):
+    a = torch.rand(n, 4, device="cuda", generator=g) * 2 - 1
+    a[:, :3] += offs
+    acts.append(a.contiguous())
+buf = (C.c_longlong * 16)()
+rows = []
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+tot = 0.0
+for t in range(steps):
+    ev0.record()
+    sim.step(acts[(t * 7) % 64])
+    ev1.record()
+    torch.cuda.synchronize()
+    tot += ev0.elapsed_time(ev1)
+    L.pih_debug_ticks(buf)
+    rows.append(list(buf)[:8])
+r = np.array(rows[50:], dtype=np.float64)
+mhz = 1965.0
+
+
+def us(a, b):
+    return float(np.median(r[:, b] - r[:, a])) / mhz
+
+
+print(f"n={n}: event mean {1e3 * tot / steps:.1f} us/step (with a sync after every step)")
+print(f"warp0  FK+apply_action(IK)         {us(0, 1):6.1f} us")
+print(f"warp1  FK+ABA+Minv+collide+rows    {us(2, 3):6.1f} us")
+print(f"warp1  barrier+motor/limit setup   {us(3, 4):6.1f} us")
+print(f"warp1  PGS                         {us(4, 5):6.1f} us")
+print(f"warp1  integrate+FK+get_info       {us(5, 7):6.1f} us")
+print(f"warp1  total (CTA 0)               {us(2, 7):6.1f} us")
