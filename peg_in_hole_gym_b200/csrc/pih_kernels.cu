@@ -137,6 +137,13 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOC
 // through a shared-memory mailbox at the motor rows.  Same arithmetic as k_step / k_rollout, bit for bit.  Every lane
 // executes the whole code (frozen / padding lanes compute on a copy and never commit) so that both warps reach the
 // barriers converged.
+// Programmatic dependent launch.  The small-batch kernels are launched with programmatic stream serialisation: once
+// every CTA of step N has passed its solver loop (pdl_trigger, in pih_step_body.inc) the CTAs of step N+1 may be
+// scheduled; they wait here until step N has completed and flushed its memory.  This overlaps the launch latency of
+// the back-to-back ~45 us kernels of a rollout with the tail of the previous step.  With any other predecessor in the
+// stream the wait returns only after that predecessor has finished (normal stream order).
+PIH_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int ARM, int TASK> PIH_D void mailbox_put(float (*mb)[32], int lane, const float* qs, const float* kpc, const float* mfc, bool fsm_done,
                                                      const EnvState& S) {
   constexpr int nb = ArmDims<ARM>::NB;
@@ -155,11 +162,13 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + lane;
   const int ec = e < P.n ? e : P.n - 1;
+  pdl_wait();
   EnvState S;
   load_state(P, ec, S);
   const bool active = (e < P.n) && !(S.flags & PIH_FLAG_DONE);
   const v3 off = env_offset(P, ec);
   PIH_TICK(w == 0 ? 0 : 2);
+  if (w == 1) PIH_TICK_CTA(0);
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
   float qs[nb], kpc[nb], mfc[nb];
@@ -176,6 +185,7 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(
   unsigned char d;
   step_back_ws<ARM, TASK>(P, S, F, qs, kpc, mfc, false, mb, lane, active, off, (unsigned)(P.env_id_base + ec), o, r, d);
   PIH_TICK(7);
+  PIH_TICK_CTA(1);
   if (active) store_state(P, e, S);
   else frozen_outputs<ARM>(S, off, o, r, d);   // done env (or a padding lane, which writes nothing below)
   if (obs) {
@@ -206,6 +216,7 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_rollout_
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int e = blockIdx.x * 32 + lane;
   const int ec = e < P.n ? e : P.n - 1;
+  pdl_wait();
   EnvState S;
   load_state(P, ec, S);
   const v3 off = env_offset(P, ec);
@@ -406,6 +417,18 @@ static cudaError_t upload_tables() {
   return cudaMemcpyToSymbol(c_arm, host, sizeof(host));
 }
 
+// launch of the small-batch kernels with programmatic stream serialisation (see pdl_wait)
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kern)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 extern "C" {
 
 int pih_abi_version(void) { return PIH_ABI_VERSION; }
@@ -517,7 +540,7 @@ const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null hand
 #define LAUNCH_WS(kern, h, st, ...)                                               \
   do {                                                                            \
     int gridw_ = ((h)->P.n + 31) / 32;                                            \
-    kern<PIH_ARM_PANDA, PIH_TASK_PEG_IN_HOLE><<<gridw_, 64, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
+    launch_pdl(kern<PIH_ARM_PANDA, PIH_TASK_PEG_IN_HOLE>, gridw_, 64, (cudaStream_t)(st), __VA_ARGS__); \
   } while (0)
 #else
 #define LAUNCH_T(kern, ARMV, h, st, ...)                                                                                \
@@ -534,9 +557,9 @@ const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null hand
   } while (0)
 #define LAUNCH_WS_T(kern, ARMV, h, st, ...)                                                                             \
   do {                                                                                                                 \
-    if ((h)->P.task == PIH_TASK_PEG_IN_HOLE) kern<ARMV, PIH_TASK_PEG_IN_HOLE><<<gridw_, 64, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
-    else if ((h)->P.task == PIH_TASK_RANDOM_FLY) kern<ARMV, PIH_TASK_RANDOM_FLY><<<gridw_, 64, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
-    else kern<ARMV, PIH_TASK_SCRIPTED><<<gridw_, 64, 0, (cudaStream_t)(st)>>>(__VA_ARGS__);                            \
+    if ((h)->P.task == PIH_TASK_PEG_IN_HOLE) launch_pdl(kern<ARMV, PIH_TASK_PEG_IN_HOLE>, gridw_, 64, (cudaStream_t)(st), __VA_ARGS__); \
+    else if ((h)->P.task == PIH_TASK_RANDOM_FLY) launch_pdl(kern<ARMV, PIH_TASK_RANDOM_FLY>, gridw_, 64, (cudaStream_t)(st), __VA_ARGS__); \
+    else launch_pdl(kern<ARMV, PIH_TASK_SCRIPTED>, gridw_, 64, (cudaStream_t)(st), __VA_ARGS__);                            \
   } while (0)
 #define LAUNCH_WS(kern, h, st, ...)                                               \
   do {                                                                            \
@@ -720,6 +743,9 @@ int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, vo
 // experiment builds only: SM clock values recorded by CTA 0 at the phase boundaries of the last step kernel
 int pih_debug_ticks(long long* out16) {
   return cudaMemcpyFromSymbol(out16, g_ticks, 16 * sizeof(long long)) == cudaSuccess ? PIH_OK : PIH_ERR_CUDA;
+}
+int pih_debug_cta_ns(unsigned long long* out2048) {
+  return cudaMemcpyFromSymbol(out2048, g_cta_ns, 2048 * sizeof(unsigned long long)) == cudaSuccess ? PIH_OK : PIH_ERR_CUDA;
 }
 #endif
 

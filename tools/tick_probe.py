@@ -26,7 +26,8 @@ for _ in range(64):
     a[:, :3] += offs
     acts.append(a.contiguous())
 buf = (C.c_longlong * 16)()
-rows = []
+cta = (C.c_ulonglong * 2048)()
+rows, ctas = [], []
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 tot = 0.0
 for t in range(steps):
@@ -37,6 +38,8 @@ for t in range(steps):
     tot += ev0.elapsed_time(ev1)
     L.pih_debug_ticks(buf)
     rows.append(list(buf)[:8])
+    L.pih_debug_cta_ns(cta)
+    ctas.append(np.array(list(cta)[:2 * ((n + 31) // 32)], dtype=np.float64).reshape(-1, 2))
 r = np.array(rows[50:], dtype=np.float64)
 mhz = 1965.0
 
@@ -52,3 +55,8 @@ print(f"warp1  barrier+motor/limit setup   {us(3, 4):6.1f} us")
 print(f"warp1  PGS                         {us(4, 5):6.1f} us")
 print(f"warp1  integrate+FK+get_info       {us(5, 7):6.1f} us")
 print(f"warp1  total (CTA 0)               {us(2, 7):6.1f} us")
+c = np.stack(ctas[50:])                      # [steps, ctas, 2] ns
+dur = (c[:, :, 1] - c[:, :, 0]) / 1e3
+span = (c[:, :, 1].max(1) - c[:, :, 0].min(1)) / 1e3
+print(f"per-CTA duration (globaltimer): median {np.median(dur):.1f} us, p90 {np.percentile(dur, 90):.1f}, max-per-step median {np.median(dur.max(1)):.1f}; "
+      f"first-start to last-end median {np.median(span):.1f} us; start skew median {np.median((c[:, :, 0].max(1) - c[:, :, 0].min(1)) / 1e3):.1f} us")
