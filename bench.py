@@ -40,8 +40,8 @@ SEED = 0
 # algorithmic cost per env-step (SURVEY.md 8d formula)
 BYTES_PER_ENV_STEP = 2 * 192 + 16 + 20 + 4 + 1   # float4-SoA state read+write (12 slots), action, obs, reward, done
 FLOPS_BULLET_DEFAULT = 2.2e5                       # I_ik=20, I_pgs=50, n=9, R=33
-NCU_EXECUTED_FLOPS_PER_ENV_STEP = 4.51e4          # ncu: (2*FFMA + FMUL + FADD thread-instructions) per launch / 4096 envs (profiles/)
-NCU_TRAFFIC_BYTES = 1016832                         # k_step_ws<panda>, 4096 envs: DRAM read 1.02 MB + write 0 B per launch (profiles/r01_kstep_ws_ncu_full.csv)
+NCU_EXECUTED_FLOPS_PER_ENV_STEP = 5.08e4          # ncu: (2*FFMA + FMUL + FADD thread-instructions) per launch / 4096 envs (profiles/r01_kstep_ws_ncu_full_v2.csv)
+NCU_TRAFFIC_BYTES = 948480                          # k_step_ws<panda>, 4096 envs: DRAM read 948 KB + write 0 B per launch (profiles/r01_kstep_ws_ncu_full_v2.csv)
 
 
 def flops_per_env_step(n=9, na=7, i_ik=20, i_pgs=50, rows=17):
@@ -269,20 +269,26 @@ def main():
     # e2e: host buffers through pih_step_host
     # e2e: the host-buffer plugin call (pih_step_host) with page-locked host buffers: every step copies that step's actions
     # H2D, runs the step, and reads (obs, reward, done) back D2H before returning
-    # (the same ring of 64 i.i.d. action batches as the device-resident arm, held in page-locked host memory; the
-    # results land in one page-locked block [obs | reward | done] that the host reads after every step)
-    h_acts, obs_h, rew_h, done_h = sim.pinned_host_buffers(n_act)
-    for b in range(n_act):
-        h_acts[b][...] = ring[b].cpu().numpy()
-    host_step = sim.host_stepper(h_acts, obs_h, rew_h, done_h)
+    # Every step gets its OWN i.i.d. action batch (action_space.sample() per step, README.md:48), pre-generated into
+    # page-locked host memory: a short repeating action sequence on one batch is a different workload (its net
+    # displacement per period accumulates and drives the arms into the table and their joint limits).  The results land
+    # in one page-locked block [obs | reward | done] that the host reads after every step.
     e2e_steps = min(args.steps, 2000)
+    e2e_warm = 20
+    h_acts, obs_h, rew_h, done_h = sim.pinned_host_buffers(e2e_steps + e2e_warm)
+    offs_np = offs.cpu().numpy()
+    rs = np.random.default_rng(4321 + rank)
+    for b in range(e2e_steps + e2e_warm):
+        h_acts[b][...] = rs.uniform(-1.0, 1.0, (n, adim)).astype(np.float32)
+        h_acts[b][:, :3] += offs_np
+    host_step = sim.host_stepper(h_acts, obs_h, rew_h, done_h)
     chk = 0.0
-    for i in range(20):
-        host_step((i * 7) % n_act)
+    for i in range(e2e_warm):
+        host_step(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        host_step((i * 7) % n_act)
+        host_step(e2e_warm + i)
         chk += float(rew_h[0]) + float(done_h[-1])      # the host consumes the step's result before the next action
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -323,11 +329,11 @@ def main():
                               if args.l2 == "rotate" else "flushed between timed steps (256 MiB memset); per-step CUDA events summed"),
                        "gather_to_rank0": bool(args.gather), "parallelism": f"env-sharded x{world}, no data-path collective"},
             "e2e": {"value": total_envs * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * adim * 4,
-                    "d2h_bytes_per_step": n * (20 + 4 + 1), "steps": e2e_steps, "timing": "wall clock per step: pih_step_host on page-locked host buffers = one launch whose SMs read that step's actions from host memory and write obs|reward|done back to host memory over PCIe (zero-copy), stream sync, host reads the result; 64 i.i.d. host action batches"},
+                    "d2h_bytes_per_step": n * (20 + 4 + 1), "steps": e2e_steps, "timing": "wall clock per step: pih_step_host on page-locked host buffers = one launch whose SMs read that step's actions from host memory and write obs|reward|done back to host memory over PCIe (zero-copy), stream sync, host reads the result; a fresh i.i.d. host action batch every step"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (ach_tf / peak_tf) if peak_tf else None, "traffic": NCU_TRAFFIC_BYTES if (args.arm == "panda" and n == ENVS_PER_GPU) else None,
-                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_kstep_ws_ncu_full.csv",
+                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_kstep_ws_ncu_full_v2.csv",
                          "peak_source": "in-run FFMA probe (pih_measure_fp32_peak); FP32 pipe is not in MEASURED_PEAKS.json",
                          "flops_per_env_step": f_run, "flops_per_env_step_bullet_default": FLOPS_BULLET_DEFAULT,
                          "executed_flops_per_env_step": NCU_EXECUTED_FLOPS_PER_ENV_STEP,

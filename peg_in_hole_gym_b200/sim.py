@@ -106,7 +106,8 @@ class BatchedSim:
         """Page-locked numpy views for the host-buffer call: `n_action_buffers` action arrays [N, A] and ONE block laid
         out [obs | reward | done] so that the results come back in a single DMA without staging copies."""
         import numpy as np
-        acts = [torch.empty(self.n, self.action_dim, dtype=torch.float32).pin_memory() for _ in range(n_action_buffers)]
+        block = torch.empty(n_action_buffers, self.n, self.action_dim, dtype=torch.float32).pin_memory()   # one allocation
+        acts = [block[i] for i in range(n_action_buffers)]
         nbytes = self.n * (self.obs_dim * 4 + 4 + 1)
         self._pinned_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         self._pinned_act = acts

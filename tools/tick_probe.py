@@ -40,6 +40,17 @@ for t in range(steps):
     rows.append(list(buf)[:8])
     L.pih_debug_cta_ns(cta)
     ctas.append(np.array(list(cta)[:2 * ((n + 31) // 32)], dtype=np.float64).reshape(-1, 2))
+    if t in (180, 190):
+        d = (ctas[-1][:, 1] - ctas[-1][:, 0]) / 1e3
+        flags = sim.int_word(11).cpu().numpy()
+        q = sim.state.cpu().numpy().transpose(1, 0, 2).reshape(n, -1)[:, 0:9]
+        order = np.argsort(-d)[:6]
+        print(f"step {t}: per-CTA us: median {np.median(d):.1f} max {d.max():.1f}; slowest CTAs:")
+        for c_ in order:
+            fl = flags[32 * c_:32 * c_ + 32] >> 8
+            qq = q[32 * c_:32 * c_ + 32]
+            print(f"   cta {c_:4d} {d[c_]:6.1f} us  pair masks {sorted(set(fl.tolist()))}  min/max q: "
+                  + " ".join(f"{qq[:, j].min():.2f}/{qq[:, j].max():.2f}" for j in range(7)))
 r = np.array(rows[50:], dtype=np.float64)
 mhz = 1965.0
 
@@ -60,3 +71,10 @@ dur = (c[:, :, 1] - c[:, :, 0]) / 1e3
 span = (c[:, :, 1].max(1) - c[:, :, 0].min(1)) / 1e3
 print(f"per-CTA duration (globaltimer): median {np.median(dur):.1f} us, p90 {np.percentile(dur, 90):.1f}, max-per-step median {np.median(dur.max(1)):.1f}; "
       f"first-start to last-end median {np.median(span):.1f} us; start skew median {np.median((c[:, :, 0].max(1) - c[:, :, 0].min(1)) / 1e3):.1f} us")
+
+# per 25-step block of the episode (all envs of the batch share the phase): where does the time go?
+print("block  IK    prologue  setup  PGS   tail   total(us)")
+for b0 in range(0, steps, 25):
+    rr = np.array(rows[b0:b0 + 25], dtype=np.float64)
+    m = lambda a, b: float(np.median(rr[:, b] - rr[:, a])) / mhz
+    print(f"{b0:5d} {m(0, 1):5.1f} {m(2, 3):8.1f} {m(3, 4):6.1f} {m(4, 5):6.1f} {m(5, 7):5.1f} {m(2, 7):7.1f}")
