@@ -503,7 +503,10 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   P.fb_iinv[0] = (float)(1.0 / ix); P.fb_iinv[1] = (float)(1.0 / iy); P.fb_iinv[2] = (float)(1.0 / iz);
   P.state = reinterpret_cast<float4*>(state_dev);
   h->block = 32;
-  h->ws = (P.n <= 148 * 32 * 2) ? 1 : 0;   // up to two 64-thread CTAs per SM: every warp still has a scheduler to itself
+  // warp-specialised kernels while a 64-thread CTA per 32 envs fits the register file (4 CTAs x 64 x 255 registers per
+  // SM): measured faster than the classic kernels up to 16384 envs for both arms (tools/ws_threshold_probe.py), slower
+  // from 24576 envs on, where the classic kernels' one warp per 32 envs fills the schedulers first
+  h->ws = (P.n <= 148 * 32 * 4) ? 1 : 0;
   const char* wse = getenv("PIH_WS");
   if (wse) h->ws = atoi(wse) ? 1 : 0;
   const char* nz = getenv("PIH_NO_ZERO_COPY");   // diagnostics: force the staged-copy host path
@@ -530,8 +533,14 @@ void pih_destroy(pih_handle* h) {
 
 const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null handle"; }
 
-#ifdef PIH_FAST_BUILD   // experiment builds (tools/): only the <panda, peg-in-hole> instantiations, a 6x shorter compile
-#define LAUNCH_T(kern, ARMV, h, st, ...) kern<PIH_ARM_PANDA, PIH_TASK_PEG_IN_HOLE><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__)
+#ifdef PIH_FAST_BUILD   // experiment builds (tools/): only ONE <arm, task> instantiation (default panda, peg-in-hole): a 6x shorter compile
+#ifndef PIH_FAST_ARM
+#define PIH_FAST_ARM PIH_ARM_PANDA
+#endif
+#ifndef PIH_FAST_TASK
+#define PIH_FAST_TASK PIH_TASK_PEG_IN_HOLE
+#endif
+#define LAUNCH_T(kern, ARMV, h, st, ...) kern<PIH_FAST_ARM, PIH_FAST_TASK><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__)
 #define LAUNCH(kern, h, st, ...)                                                  \
   do {                                                                            \
     int grid_ = ((h)->P.n + (h)->block - 1) / (h)->block;                         \
@@ -540,7 +549,7 @@ const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null hand
 #define LAUNCH_WS(kern, h, st, ...)                                               \
   do {                                                                            \
     int gridw_ = ((h)->P.n + 31) / 32;                                            \
-    launch_pdl(kern<PIH_ARM_PANDA, PIH_TASK_PEG_IN_HOLE>, gridw_, 64, (cudaStream_t)(st), __VA_ARGS__); \
+    launch_pdl(kern<PIH_FAST_ARM, PIH_FAST_TASK>, gridw_, 64, (cudaStream_t)(st), __VA_ARGS__); \
   } while (0)
 #else
 #define LAUNCH_T(kern, ARMV, h, st, ...)                                                                                \

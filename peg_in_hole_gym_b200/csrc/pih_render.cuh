@@ -8,24 +8,73 @@ namespace pih {
 
 #define PIH_RENDER_PPT 8
 
-// Conservative screen-space rectangle (pixel rows/cols) of a bounding sphere (centre c, radius R) seen from eye e by
-// the straight-down camera (camera axes == env axes).  Used only to skip ray tests that cannot hit; never culls a hit.
-PIH_D void screen_rect(v3 e, v3 c, float R, int W, int H, float* out4) {
-  const float ith = 1.0f / (float)PIH_CAM_TAN_HALF_FOV;
-  float dx = c.x - e.x, dy = c.y - e.y, dz = e.z - c.z;
-  R = R * 1.05f + 1e-4f;
-  float r0 = 0.0f, r1 = (float)(H - 1), c0 = 0.0f, c1 = (float)(W - 1);
-  if (dz + R <= 0.0f) { c0 = 1.0f; c1 = 0.0f; }            // entirely behind the camera: empty rectangle
-  else if (dz - R > 1e-3f) {
-    float zn = dz - R, zf = dz + R;
-    float xlo = (dx - R) * ith / ((dx - R >= 0.0f) ? zf : zn), xhi = (dx + R) * ith / ((dx + R >= 0.0f) ? zn : zf);
-    float ylo = (dy - R) * ith / ((dy - R >= 0.0f) ? zf : zn), yhi = (dy + R) * ith / ((dy + R >= 0.0f) ? zn : zf);
-    c0 = fmaxf(c0, floorf((xlo + 1.0f) * 0.5f * (float)W - 0.5f) - 1.0f);
-    c1 = fminf(c1, ceilf((xhi + 1.0f) * 0.5f * (float)W - 0.5f) + 1.0f);
-    r0 = fmaxf(r0, floorf((1.0f - yhi) * 0.5f * (float)H - 0.5f) - 1.0f);
-    r1 = fminf(r1, ceilf((1.0f - ylo) * 0.5f * (float)H - 0.5f) + 1.0f);
+// Conservative screen rectangle of an oriented box (centre c, axes = columns of R, half extents h): the box is clipped
+// against the plane just in front of the eye (no ray parameter below the near distance is accepted, so nothing behind
+// it can be hit), and the rectangle bounds the projections of the corners in front of that plane and of the points
+// where edges cross it.  Unlike the bounding-sphere bound this stays tight for bodies next to the camera (the fingers
+// and a grasped peg sit within centimetres of the eye, mostly above it).  Never culls a hit.
+PIH_D void screen_rect_box(v3 e, const m3& R, v3 c, v3 h, int W, int H, float* out4) {
+  const float ith = 1.0f / (float)PIH_CAM_TAN_HALF_FOV, zc = 0.5f * (float)PIH_CAM_NEAR;
+  h = mk(h.x * 1.02f + 1e-4f, h.y * 1.02f + 1e-4f, h.z * 1.02f + 1e-4f);
+  float px[8], py[8], pz[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    v3 l = mk((k & 1) ? h.x : -h.x, (k & 2) ? h.y : -h.y, (k & 4) ? h.z : -h.z);
+    v3 w = mv_add(R, l, c);
+    px[k] = w.x - e.x; py[k] = w.y - e.y; pz[k] = e.z - w.z;   // pz: depth along the viewing direction
+  }
+  float xlo = 1e30f, xhi = -1e30f, ylo = 1e30f, yhi = -1e30f;
+  auto add = [&](float x, float y, float z) {
+    float iz = ith / z;
+    float u = x * iz, v = y * iz;
+    xlo = fminf(xlo, u); xhi = fmaxf(xhi, u); ylo = fminf(ylo, v); yhi = fmaxf(yhi, v);
+  };
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (pz[k] > zc) add(px[k], py[k], pz[k]);
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const int m = k ^ (1 << a);
+      if (m < k) continue;                                      // each of the 12 edges once
+      if ((pz[k] > zc) != (pz[m] > zc)) {
+        float t = (zc - pz[k]) / (pz[m] - pz[k]);
+        add(fmaf(t, px[m] - px[k], px[k]), fmaf(t, py[m] - py[k], py[k]), zc);
+      }
+    }
+  float r0 = 1.0f, r1 = 0.0f, c0 = 1.0f, c1 = 0.0f;              // empty rectangle: the whole box is behind the eye
+  if (xlo <= xhi) {
+    // clamp in normalised coordinates first (clipped points can project arbitrarily far out)
+    xlo = fmaxf(xlo, -2.0f); xhi = fminf(xhi, 2.0f); ylo = fmaxf(ylo, -2.0f); yhi = fminf(yhi, 2.0f);
+    c0 = fmaxf(0.0f, floorf((xlo + 1.0f) * 0.5f * (float)W - 0.5f) - 1.0f);
+    c1 = fminf((float)(W - 1), ceilf((xhi + 1.0f) * 0.5f * (float)W - 0.5f) + 1.0f);
+    r0 = fmaxf(0.0f, floorf((1.0f - yhi) * 0.5f * (float)H - 0.5f) - 1.0f);
+    r1 = fminf((float)(H - 1), ceilf((1.0f - ylo) * 0.5f * (float)H - 0.5f) + 1.0f);
   }
   out4[0] = r0; out4[1] = r1; out4[2] = c0; out4[3] = c1;
+}
+
+// depth-buffer value and shaded colour of a hit (obj < 0: nothing hit) - the tail of the oracle's render_pixel
+PIH_D float4 shade_pixel(int obj, float best, v3 nb) {
+  const float fn = (float)PIH_CAM_FAR, nn = (float)PIH_CAM_NEAR;
+  float depth = 1.0f, r = 255.0f, g = 255.0f, bl = 255.0f, shade = 1.0f;
+  if (obj >= 0) {
+    depth = fmaf(0.5f, (fn + nn) / (fn - nn) - (2.0f * fn * nn) / ((fn - nn) * best), 0.5f);
+    r = (obj == 0) ? 153.0f : (obj == 3) ? 204.0f : 232.0f;
+    g = (obj == 0) ? 128.0f : (obj == 3) ? 204.0f : 232.0f;
+    bl = (obj == 0) ? 102.0f : (obj == 3) ? 204.0f : 232.0f;
+    const v3 l = mk((float)0.2672612419124244, (float)0.1781741612749496, (float)0.9449111825230680);
+    float nl = vdot(nb, l);
+    nl = (nl < 0.0f) ? 0.0f : nl;
+    shade = fmaf(0.65f, nl, 0.35f);
+  }
+  float4 px;
+  px.x = depth;
+  px.y = (float)(int)(r * shade + 0.5f);
+  px.z = (float)(int)(g * shade + 0.5f);
+  px.w = (float)(int)(bl * shade + 0.5f);
+  return px;
 }
 
 // scene block per env: eye(3) Rfb(9) pfb(3) Rbox0(9) cbox0(3) Rbox1(9) cbox1(3) | 39: screen rects (r0,r1,c0,c1) of the
@@ -55,10 +104,21 @@ template <int ARM> __global__ void __launch_bounds__(128) k_scene(SimParams P, f
 #pragma unroll
     for (int i = 0; i < 9; ++i) o[15 + 12 * b + i] = Rb.m[i / 3][i % 3];
     o[24 + 12 * b] = cb.x; o[25 + 12 * b] = cb.y; o[26 + 12 * b] = cb.z;
-    screen_rect(eye, cb, T.box_h[b][0] + T.box_h[b][1] + T.box_h[b][2], W, H, o + 47 + 4 * b);
+    screen_rect_box(eye, Rb, cb, ld3(T.box_h[b]), W, H, o + 47 + 4 * b);
   });
-  screen_rect(eye, mk(S.ppos[0], S.ppos[1], S.ppos[2]), P.fb_half[0] + P.fb_half[1] + P.fb_half[2], W, H, o + 39);
-  screen_rect(eye, mk((float)PIH_HOLE_X, (float)PIH_HOLE_Y, (float)PIH_HOLE_Z), (float)(PIH_HOLE_ROUT + PIH_HOLE_HL), W, H, o + 43);
+  // free body: its own box, or the box around the peg cylinder (fb_half = (r, half length, r), axis = local y)
+  screen_rect_box(eye, Rfb, mk(S.ppos[0], S.ppos[1], S.ppos[2]), mk(P.fb_half[0], P.fb_half[1], P.fb_half[2]), W, H, o + 39);
+  {  // hole: box around the tube (axis = env x)
+    m3 I3;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) I3.m[i / 3][i % 3] = (i / 3 == i % 3) ? 1.0f : 0.0f;
+    screen_rect_box(eye, I3, mk((float)PIH_HOLE_X, (float)PIH_HOLE_Y, (float)PIH_HOLE_Z),
+                    mk((float)PIH_HOLE_HL, (float)PIH_HOLE_ROUT, (float)PIH_HOLE_ROUT), W, H, o + 43);
+  }
+  // words 55..58: the pixel of a ray that hits nothing but the table.  The camera looks straight down, so the ray
+  // parameter of the table plane (eye-space depth) and its shading are the same for every pixel of the env.
+  float4 bg = shade_pixel(eye.z - (float)PIH_TABLE_Z > (float)PIH_CAM_NEAR ? 0 : -1, eye.z - (float)PIH_TABLE_Z, mk(0.0f, 0.0f, 1.0f));
+  o[55] = bg.x; o[56] = bg.y; o[57] = bg.z; o[58] = bg.w;
 }
 
 PIH_D bool ray_box(v3 o, v3 d, v3 h, float smin, float& s_hit, v3& n) {
@@ -160,82 +220,79 @@ PIH_D bool near_sphere(v3 o, v3 d, v3 c, float rad) {
   return perp2 <= rad * rad * dd * 1.1f + 1e-9f;
 }
 
-template <int ARM, int TASK> __global__ void __launch_bounds__(256, 4) k_render(SimParams P, const float* __restrict__ scene, int W, int H,
-                                                                          float4* __restrict__ out) {
+// One float4 (depth, r, g, b) per pixel, PIH_RENDER_PPT pixels per thread strided by the block size so that every warp
+// store is 512 contiguous bytes.  Most pixels see only the table: a warp none of whose 32 pixels lies inside the screen
+// rectangle of an object stores the env's background pixel (computed once by k_scene) without casting a ray, which is
+// what lets the kernel run at the HBM write rate; the others run the full ray caster (same formulas as the oracle).
+template <int ARM, int TASK> __global__ void __launch_bounds__(256) k_render(SimParams P, const float* __restrict__ scene, int W, int H,
+                                                                       float4* __restrict__ out) {
   __shared__ float sc[PIH_SCENE_WORDS];
   const int e = blockIdx.y;
   if (threadIdx.x < PIH_SCENE_WORDS) sc[threadIdx.x] = scene[(size_t)PIH_SCENE_WORDS * e + threadIdx.x];
   __syncthreads();
-  // PIH_RENDER_PPT pixels per thread, strided by the block size so that every warp store is 512 contiguous bytes
   const ArmTables& T = c_arm[ARM];
+  const float4 bg = make_float4(sc[55], sc[56], sc[57], sc[58]);
+  const float invW = 1.0f / (float)W;
+  const int npix = W * H;
+  float4* __restrict__ img = out + (size_t)e * npix;
+#define IN_RECT(base) (frow >= sc[(base)] && frow <= sc[(base) + 1] && fcol >= sc[(base) + 2] && fcol <= sc[(base) + 3])
 #pragma unroll 1
   for (int it = 0; it < PIH_RENDER_PPT; ++it) {
-  const int pix = (blockIdx.x * PIH_RENDER_PPT + it) * blockDim.x + threadIdx.x;
-  if (pix >= W * H) return;
-  const int row = pix / W, col = pix - row * W;
-  const float frow = (float)row, fcol = (float)col;
-#define IN_RECT(base) (frow >= sc[(base)] && frow <= sc[(base) + 1] && fcol >= sc[(base) + 2] && fcol <= sc[(base) + 3])
-  const float th = (float)PIH_CAM_TAN_HALF_FOV;
-  float ndx = ((float)col + 0.5f) / (float)W * 2.0f - 1.0f;
-  float ndy = 1.0f - ((float)row + 0.5f) / (float)H * 2.0f;
-  v3 d = mk(ndx * th, ndy * th, -1.0f);
-  v3 o = mk(sc[0], sc[1], sc[2]);
-  const float smin = (float)PIH_CAM_NEAR;
-  float best = 1e30f;
-  v3 nb = mk(0.0f, 0.0f, 1.0f);
-  int obj = -1;
-  { float s = o.z - (float)PIH_TABLE_Z; if (s > smin) { best = s; obj = 0; } }
-  {
-    m3 Rfb;
+    const int pix = (blockIdx.x * PIH_RENDER_PPT + it) * blockDim.x + threadIdx.x;
+    const bool valid = pix < npix;
+    // row = pix / W without an integer division: exact for images up to 4096 x 4096 (error 4e-5 against a margin 0.5/W)
+    const int row = (int)(((float)pix + 0.5f) * invW), col = pix - row * W;
+    const float frow = (float)row, fcol = (float)col;
+    bool near_obj = valid && (IN_RECT(39) || (ArmGeom<ARM>::NBOX > 0 && IN_RECT(47)) || (ArmGeom<ARM>::NBOX > 1 && IN_RECT(51)));
+    if (TASK != PIH_TASK_RANDOM_FLY) near_obj = near_obj || (valid && IN_RECT(43));
+    float4 px = bg;
+    if (__any_sync(0xffffffffu, near_obj)) {
+      if (near_obj) {
+        const float th = (float)PIH_CAM_TAN_HALF_FOV;
+        float ndx = ((float)col + 0.5f) / (float)W * 2.0f - 1.0f;
+        float ndy = 1.0f - ((float)row + 0.5f) / (float)H * 2.0f;
+        v3 d = mk(ndx * th, ndy * th, -1.0f);
+        v3 o = mk(sc[0], sc[1], sc[2]);
+        const float smin = (float)PIH_CAM_NEAR;
+        float best = 1e30f;
+        v3 nb = mk(0.0f, 0.0f, 1.0f);
+        int obj = -1;
+        { float s = o.z - (float)PIH_TABLE_Z; if (s > smin) { best = s; obj = 0; } }
+        if (IN_RECT(39)) {
+          m3 Rfb;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Rfb.m[i / 3][i % 3] = sc[3 + i];
-    v3 pfb = mk(sc[12], sc[13], sc[14]);
-    if (IN_RECT(39)) {
-      v3 ol = mTv(Rfb, vsub(o, pfb)), dl = mTv(Rfb, d);
-      float s; v3 n; bool h;
-      if (TASK != PIH_TASK_RANDOM_FLY) h = ray_cyl_y(ol, dl, P.fb_half[0], P.fb_half[1], smin, s, n);
-      else h = ray_box(ol, dl, mk(P.fb_half[0], P.fb_half[1], P.fb_half[2]), smin, s, n);
-      if (h && s < best) { best = s; obj = 1; nb = mv(Rfb, n); }
-    }
-  }
-  if (TASK != PIH_TASK_RANDOM_FLY) {
-    if (IN_RECT(43)) {
-      v3 oh = mk(o.x - (float)PIH_HOLE_X, o.y - (float)PIH_HOLE_Y, o.z - (float)PIH_HOLE_Z);
-      float s; v3 n;
-      if (ray_tube_x(oh, d, smin, s, n) && s < best) { best = s; obj = 2; nb = n; }
-    }
-  }
+          for (int i = 0; i < 9; ++i) Rfb.m[i / 3][i % 3] = sc[3 + i];
+          v3 pfb = mk(sc[12], sc[13], sc[14]);
+          v3 ol = mTv(Rfb, vsub(o, pfb)), dl = mTv(Rfb, d);
+          float s; v3 n; bool h;
+          if (TASK != PIH_TASK_RANDOM_FLY) h = ray_cyl_y(ol, dl, P.fb_half[0], P.fb_half[1], smin, s, n);
+          else h = ray_box(ol, dl, mk(P.fb_half[0], P.fb_half[1], P.fb_half[2]), smin, s, n);
+          if (h && s < best) { best = s; obj = 1; nb = mv(Rfb, n); }
+        }
+        if (TASK != PIH_TASK_RANDOM_FLY) {
+          if (IN_RECT(43)) {
+            v3 oh = mk(o.x - (float)PIH_HOLE_X, o.y - (float)PIH_HOLE_Y, o.z - (float)PIH_HOLE_Z);
+            float s; v3 n;
+            if (ray_tube_x(oh, d, smin, s, n) && s < best) { best = s; obj = 2; nb = n; }
+          }
+        }
 #pragma unroll
-  for (int b = 0; b < ArmGeom<ARM>::NBOX; ++b) {
-    m3 Rb;
+        for (int b = 0; b < ArmGeom<ARM>::NBOX; ++b) {
+          if (IN_RECT(47 + 4 * b)) {
+            m3 Rb;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) Rb.m[i / 3][i % 3] = sc[15 + 12 * b + i];
-    v3 cb = mk(sc[24 + 12 * b], sc[25 + 12 * b], sc[26 + 12 * b]);
-    v3 hb = ld3(T.box_h[b]);
-    if (IN_RECT(47 + 4 * b)) {
-      v3 ol = mTv(Rb, vsub(o, cb)), dl = mTv(Rb, d);
-      float s; v3 n;
-      if (ray_box(ol, dl, hb, smin, s, n) && s < best) { best = s; obj = 3; nb = mv(Rb, n); }
+            for (int i = 0; i < 9; ++i) Rb.m[i / 3][i % 3] = sc[15 + 12 * b + i];
+            v3 cb = mk(sc[24 + 12 * b], sc[25 + 12 * b], sc[26 + 12 * b]);
+            v3 hb = ld3(T.box_h[b]);
+            v3 ol = mTv(Rb, vsub(o, cb)), dl = mTv(Rb, d);
+            float s; v3 n;
+            if (ray_box(ol, dl, hb, smin, s, n) && s < best) { best = s; obj = 3; nb = mv(Rb, n); }
+          }
+        }
+        px = shade_pixel(obj, best, nb);
+      }
     }
-  }
-  const float fn = (float)PIH_CAM_FAR, nn = (float)PIH_CAM_NEAR;
-  float depth = 1.0f, r = 255.0f, g = 255.0f, bl = 255.0f, shade = 1.0f;
-  if (obj >= 0) {
-    depth = fmaf(0.5f, (fn + nn) / (fn - nn) - (2.0f * fn * nn) / ((fn - nn) * best), 0.5f);
-    r = (obj == 0) ? 153.0f : (obj == 3) ? 204.0f : 232.0f;
-    g = (obj == 0) ? 128.0f : (obj == 3) ? 204.0f : 232.0f;
-    bl = (obj == 0) ? 102.0f : (obj == 3) ? 204.0f : 232.0f;
-    const v3 l = mk((float)0.2672612419124244, (float)0.1781741612749496, (float)0.9449111825230680);
-    float nl = vdot(nb, l);
-    nl = (nl < 0.0f) ? 0.0f : nl;
-    shade = fmaf(0.65f, nl, 0.35f);
-  }
-  float4 px;
-  px.x = depth;
-  px.y = (float)(int)(r * shade + 0.5f);
-  px.z = (float)(int)(g * shade + 0.5f);
-  px.w = (float)(int)(bl * shade + 0.5f);
-  out[(size_t)e * W * H + pix] = px;
+    if (valid) __stcs(&img[pix], px);   // written once, never re-read by this kernel: streaming store
   }
 #undef IN_RECT
 }

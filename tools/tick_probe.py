@@ -15,14 +15,16 @@ from peg_in_hole_gym_b200.sim import BatchedSim  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 400
+arm = sys.argv[3] if len(sys.argv) > 3 else "panda"
+adim = 4 if arm == "panda" else 6
 L = _native.lib()
-sim = BatchedSim(n, offset=(2.0, 3.0, 0.0), max_steps=200, auto_reset=True, seed=0, device=0)
+sim = BatchedSim(n, arm=arm, offset=(2.0, 3.0, 0.0), max_steps=200, auto_reset=True, seed=0, device=0)
 sim.reset()
 offs = sim.env_offsets().cuda()
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 acts = []
-for _ in range(64):
-    a = torch.rand(n, 4, device="cuda", generator=g) * 2 - 1
+for _ in range(steps):
+    a = torch.rand(n, adim, device="cuda", generator=g) * 2 - 1
     a[:, :3] += offs
     acts.append(a.contiguous())
 buf = (C.c_longlong * 16)()
@@ -32,7 +34,7 @@ ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=
 tot = 0.0
 for t in range(steps):
     ev0.record()
-    sim.step(acts[(t * 7) % 64])
+    sim.step(acts[t])
     ev1.record()
     torch.cuda.synchronize()
     tot += ev0.elapsed_time(ev1)
@@ -50,7 +52,7 @@ for t in range(steps):
             fl = flags[32 * c_:32 * c_ + 32] >> 8
             qq = q[32 * c_:32 * c_ + 32]
             print(f"   cta {c_:4d} {d[c_]:6.1f} us  pair masks {sorted(set(fl.tolist()))}  min/max q: "
-                  + " ".join(f"{qq[:, j].min():.2f}/{qq[:, j].max():.2f}" for j in range(7)))
+                  + " ".join(f"{qq[:, j].min():.2f}/{qq[:, j].max():.2f}" for j in range(6)))
 r = np.array(rows[50:], dtype=np.float64)
 mhz = 1965.0
 
