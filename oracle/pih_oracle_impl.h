@@ -1367,9 +1367,11 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
           real rel = RC(0);
           if (r->has_fb) rel = FN(v3_dot)(r->dir[d], dvl) + FN(v3_dot)(r->jang[d], dvw);
           if (r->arm_body >= 0) {
-            real ra = RC(0);
-            for (int j = 0; j < nb; ++j) ra = FMA(r->ja[d][j], dva[j], ra);
-            rel = rel + ra;
+            /* J_arm . dva as two interleaved partial sums (even / odd joints) */
+            real s0 = RC(0), s1 = RC(0);
+            for (int j = 0; j < nb; j += 2) s0 = FMA(r->ja[d][j], dva[j], s0);
+            for (int j = 1; j < nb; j += 2) s1 = FMA(r->ja[d][j], dva[j], s1);
+            rel = r->has_fb ? rel + (s0 + s1) : (s0 + s1);
           }
           real dl = FMA(-rel, r->dinv[d], r->b[d]);
           if (d == 0) PIH_PROJECT_LO(dl, r->lam[d]);
