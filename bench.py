@@ -340,7 +340,7 @@ def main():
                          "achieved_executed": NCU_EXECUTED_FLOPS_PER_ENV_STEP * n / kern_s / 1e12,
                          "frac_executed": (NCU_EXECUTED_FLOPS_PER_ENV_STEP * n / kern_s / 1e12 / peak_tf) if peak_tf else None,
                          "note": "achieved/frac use SURVEY 8(d)'s algorithmic FLOP model; *_executed use the FP32 thread-instructions ncu counted "
-                                 "(the implementation skips structural zeros and reuses the ABA factorisation, so it executes ~3x fewer)",
+                                 "(the implementation skips structural zeros and reuses the ABA factorisation, so it executes well under half)",
                          "kernel": ("pih::k_step_ws" if n <= 148 * 64 else "pih::k_step") + f"<{args.arm}, {args.task}>", "kernel_us": kern_s * 1e6,
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"}},

@@ -16,10 +16,15 @@ from peg_in_hole_gym_b200.sim import BatchedSim  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 400
 arm = sys.argv[3] if len(sys.argv) > 3 else "panda"
+task = sys.argv[4] if len(sys.argv) > 4 else "peg-in-hole"
+preroll = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 adim = 4 if arm == "panda" else 6
 L = _native.lib()
-sim = BatchedSim(n, arm=arm, offset=(2.0, 3.0, 0.0), max_steps=200, auto_reset=True, seed=0, device=0)
+sim = BatchedSim(n, arm=arm, task=task, offset=(2.0, 3.0, 0.0), max_steps=0 if task.endswith("scripted") else 200,
+                 auto_reset=not task.endswith("scripted"), seed=0, device=0)
 sim.reset()
+if preroll:
+    sim.rollout(preroll, count=False)
 offs = sim.env_offsets().cuda()
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 acts = []
