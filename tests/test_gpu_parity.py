@@ -121,6 +121,42 @@ def test_panda_scripted_grasp_contacts_bit_exact():
     assert seen & (4 | 8), "finger-peg contact expected"
 
 
+@pytest.mark.parametrize("arm", ["panda", "ur5"])
+def test_mixed_contact_types_inside_one_warp_bit_exact(arm):
+    """The small-batch kernels choose their solver path per WARP (free-body island before the barrier, arm-only rows,
+    general rows when some lane couples its islands).  Interleave envs that grasp the peg (coupled), envs that press
+    the arm onto the table away from the peg (arm rows only) and envs that move randomly, so that every warp holds all
+    three kinds at once; everything must still equal the oracle bit for bit."""
+    n = 96
+    sim, orc = _pair(n, arm=arm, offset=(2.0, 3.0, 0.0), seed=31)
+    sim.reset(); orc.reset()
+    offs = sim.env_offsets().numpy()
+    peg = ol.state_field(orc.get_state(), ol.S_PPOS, 3)[:, :2]
+    adim = 4 if arm == "panda" else 6
+    rng = np.random.default_rng(17)
+    kind = np.arange(n) % 3                      # 0 grasp, 1 press on the table, 2 random
+    acts = []
+    for t in range(240):
+        a = rng.uniform(-1, 1, (n, adim)).astype(np.float32)
+        z = 0.25 if t < 60 else -0.02 if t < 150 else -0.1
+        g = kind == 0
+        a[g, 0:2] = peg[g]; a[g, 2] = z
+        p_ = kind == 1
+        a[p_, 0] = 0.45; a[p_, 1] = 0.25; a[p_, 2] = -0.2 if t > 30 else 0.2
+        if arm == "panda":
+            a[g, 3] = 0.04 if t < 170 else 0.0
+            a[p_, 3] = 0.02
+        else:
+            a[g | p_, 3:6] = np.array([0.0, 3.14159, 0.0], np.float32)
+        a[:, :3] += offs
+        acts.append(a)
+    _run_compare(sim, orc, acts, reset=False)
+    masks = (sim.int_word(11).cpu().numpy() >> 8) & 0xff
+    assert (masks[kind == 1] & 16).any(), "arm-table contact expected in the pressing envs"
+    if arm == "panda":
+        assert (masks[kind == 0] & (4 | 8)).any(), "finger-peg contact expected in the grasping envs"
+
+
 def test_peg_dropped_into_hole_region_contacts_bit_exact():
     n = 64
     sim, orc = _pair(n, offset=(2.0, 3.0, 0.0), seed=8)
