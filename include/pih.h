@@ -104,6 +104,14 @@ int pih_ee_pose(pih_handle* h, float* pos_dev, float* rot_dev, void* stream);
  * the layout of the reference's np.concatenate((depth, rgb), 2).  The reference renders 300 x 300. */
 int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, void* stream);
 
+/* The label images of the shipped task's random_grasp (peg_in_hole.py:41-45,65-98), for every env: a rotated
+ * rectangle (half extents 0.1 x 0.2 in normalised image units; angle captured by the scripted state machine when it
+ * entered state 2) filled into labels_dev float[num_envs][4][height][width] = (pos_img: 50 inside, sin(2 angle),
+ * cos(2 angle): 1 outside, wid_img: rectangle width in pixels); params_dev (nullable) float[num_envs][5] =
+ * (x = 0, y = 0, angle in degrees, width, length in pixels), the second element of the reference's return value.
+ * Before state 2 has been entered the images are the reference's initial ones (zeros, cos = 1). */
+int pih_grasp_labels(pih_handle* h, int32_t width, int32_t height, float* labels_dev, float* params_dev, void* stream);
+
 /* FP32 FMA-throughput micro-benchmark (roofline denominator): returns measured TFLOP/s. */
 int pih_measure_fp32_peak(int device, double* tflops_out);
 

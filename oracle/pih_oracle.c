@@ -1,6 +1,7 @@
 /* CPU ORACLE driver - TEST INFRASTRUCTURE ONLY (see pih_oracle_impl.h header: PARITY UNPINNED vs PyBullet).
  * Batched wrapper around the per-env restatement: BaseEnvMp.step / BaseEnv.step loop semantics
  * (peg_in_hole_gym/envs/base_env_mp.py:40-63, peg_in_hole_gym/envs/base_env.py:35-94). */
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -219,6 +220,7 @@ int pih_oracle_get_state(void* h, float* words) {
       memcpy(&words[WIDX(PIH_S_FSM_STATE, i, n)], &fs, 4);
       memcpy(&words[WIDX(PIH_S_FSM_T, i, n)], &ft, 4);
       words[WIDX(PIH_S_RANDY, i, n)] = o->use_double ? (float)o->sd[i].rand_y : o->sf[i].rand_y;
+      words[WIDX(PIH_S_GRASP_ANG, i, n)] = o->use_double ? (float)o->sd[i].grasp_ang : o->sf[i].grasp_ang;
       for (int k = 0; k < 7; ++k) words[WIDX(PIH_S_MTGT + k, i, n)] = o->use_double ? (float)o->sd[i].mtgt[k] : o->sf[i].mtgt[k];
     }
     ints[0] = o->use_double ? o->sd[i].step : o->sf[i].step;
@@ -255,6 +257,7 @@ int pih_oracle_set_state(void* h, const float* words) {
       memcpy(&ft, &words[WIDX(PIH_S_FSM_T, i, n)], 4);
       o->sf[i].fsm_state = o->sd[i].fsm_state = fs; o->sf[i].fsm_t = o->sd[i].fsm_t = ft;
       o->sf[i].rand_y = words[WIDX(PIH_S_RANDY, i, n)]; o->sd[i].rand_y = o->sf[i].rand_y;
+      o->sf[i].grasp_ang = words[WIDX(PIH_S_GRASP_ANG, i, n)]; o->sd[i].grasp_ang = o->sf[i].grasp_ang;
       for (int k = 0; k < 7; ++k) { o->sf[i].mtgt[k] = words[WIDX(PIH_S_MTGT + k, i, n)]; o->sd[i].mtgt[k] = o->sf[i].mtgt[k]; }
     }
     o->sf[i].step = o->sd[i].step = ints[0];
@@ -333,6 +336,56 @@ int pih_oracle_model_nb(int arm) { return arm == PIH_ARM_PANDA ? PIH_PANDA_NB : 
 
 void pih_oracle_sincos(float x, float* s, float* c) { pih_sincosf_det(x, s, c); }
 float pih_oracle_atan2_q1(float y, float x) { return det_atan2_q1_f(y, x); }
+
+/* Label images of random_grasp (peg_in_hole.py:41-45,65-98) for envs [lo, hi): labels float[hi-lo][4][H][W] =
+ * (pos_img, sin_img, cos_img, wid_img), params float[hi-lo][5] = (x, y, angle in degrees, width, length).  The rectangle
+ * a, c, b, d of peg_in_hole.py:78-83 (first coordinate <-> column, second <-> row, because the reference writes
+ * pos_img[cc, rr]) is filled where the integer pixel lies inside the closed quad (skimage.draw.polygon [3P]: interior
+ * plus boundary).  Float arithmetic, same operation order as the CUDA kernel. */
+int pih_oracle_grasp_labels(void* h, int W, int H, int lo, int hi, float* labels, float* params) {
+  oracle* o = (oracle*)h;
+  for (int i = lo; i < hi; ++i) {
+    float ang = o->use_double ? (float)o->sd[i].grasp_ang : o->sf[i].grasp_ang;
+    int any = ang > (float)(0.5 * PIH_LABEL_NONE);
+    float sa, ca, s2, c2;
+    det_sincos_f(any ? ang : 0.0f, &sa, &ca);
+    det_sincos_f(any ? 2.0f * ang : 0.0f, &s2, &c2);
+    const float L = (float)PIH_LABEL_LENGTH, Wd = (float)PIH_LABEL_WIDTH, S0 = (float)W, S1 = (float)H;
+    float vx[4], vy[4];
+    vx[0] = (1.0f + L * ca + Wd * sa) / 2.0f * S0; vy[0] = (1.0f - L * sa + Wd * ca) / 2.0f * S1;
+    vx[1] = (1.0f - L * ca + Wd * sa) / 2.0f * S0; vy[1] = (1.0f + L * sa + Wd * ca) / 2.0f * S1;
+    vx[2] = (1.0f - L * ca - Wd * sa) / 2.0f * S0; vy[2] = (1.0f + L * sa - Wd * ca) / 2.0f * S1;
+    vx[3] = (1.0f + L * ca - Wd * sa) / 2.0f * S0; vy[3] = (1.0f - L * sa - Wd * ca) / 2.0f * S1;
+    float dx = vx[0] - vx[3], dy = vy[0] - vy[3];
+    float wid = sqrtf(fmaf(dx, dx, dy * dy));
+    dx = vx[0] - vx[1]; dy = vy[0] - vy[1];
+    float len = sqrtf(fmaf(dx, dx, dy * dy));
+    if (params) {
+      float* p = params + 5 * (size_t)(i - lo);
+      p[0] = 0.0f; p[1] = 0.0f;
+      p[2] = any ? ang / (float)3.141592653589793 * 180.0f : 0.0f;
+      p[3] = any ? wid : 0.0f; p[4] = any ? len : 0.0f;
+    }
+    float* img = labels + (size_t)(i - lo) * 4 * H * W;
+    const size_t np = (size_t)H * W;
+    for (int r = 0; r < H; ++r)
+      for (int c = 0; c < W; ++c) {
+        int pos = 1, neg = 1;
+        for (int k = 0; k < 4; ++k) {
+          int m = (k + 1) & 3;
+          float cr = fmaf(vx[m] - vx[k], (float)r - vy[k], -((vy[m] - vy[k]) * ((float)c - vx[k])));
+          pos = pos && (cr >= 0.0f); neg = neg && (cr <= 0.0f);
+        }
+        int in = any && (pos || neg);
+        size_t px = (size_t)r * W + c;
+        img[px] = in ? (float)PIH_LABEL_POS_VALUE : 0.0f;
+        img[np + px] = in ? s2 : 0.0f;
+        img[2 * np + px] = in ? c2 : 1.0f;
+        img[3 * np + px] = in ? wid : 0.0f;
+      }
+  }
+  return 0;
+}
 
 /* PegInHole.render for envs [lo, hi): out float[hi-lo][H][W][4] = (depth, r, g, b) */
 int pih_oracle_render(void* h, int W, int H, int lo, int hi, float* out) {

@@ -332,6 +332,7 @@ typedef struct {
   int32_t step, episode, flags;
   int32_t fsm_state, fsm_t;   /* scripted task */
   real rand_y, mtgt[7];
+  real grasp_ang;             /* captured on entering FSM state 2 (peg_in_hole.py:65-72) */
 } FN(envstate);
 #define envstate FN(envstate)
 
@@ -942,6 +943,7 @@ static void FN(reset_env)(const model* M, const simcfg* C, envstate* S, uint32_t
   /* scripted task: cur_state 0, random_vector = [0, U(-0.03, 0.03), 0] (peg_in_hole.py:255-267) */
   S->fsm_state = 0; S->fsm_t = 0;
   S->rand_y = (real)fmaf(u[3], 0.06f, -0.03f);
+  S->grasp_ang = RC(PIH_LABEL_NONE);
   for (int i = 0; i < 7; ++i) S->mtgt[i] = (i < M->narm) ? M->rest[i] : RC(0);
 }
 
@@ -1139,7 +1141,8 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
      * scripted grasp->insert state machine of random_grasp/grasp_process (peg_in_hole.py:39-212).  One engine step
      * here = one pass of its `while not done` loop body: update_state, grasp target, grasp_process, stepSimulation. */
     static const int fsm_steps[PIH_FSM_NSTATES] = {PIH_FSM_STEPS_LIST};
-    if (S->fsm_t == fsm_steps[S->fsm_state]) {                      /* update_state, peg_in_hole.py:206-212 */
+    const int entered = (S->fsm_t == fsm_steps[S->fsm_state]);
+    if (entered) {                                                   /* update_state, peg_in_hole.py:206-212 */
       S->fsm_state += 1; S->fsm_t = 0;
       if (S->fsm_state >= PIH_FSM_NSTATES) S->fsm_state = 0;
     }
@@ -1147,6 +1150,9 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
     const int st = S->fsm_state;
     /* grasp point = COM of the grasp link + R(q) random_vector; yaw of that link (peg_in_hole.py:58-62,125,215-225) */
     m3 Rp = FN(quat_to_m3)(S->pquat);
+    /* on entering state 2 the reference captures the grasp image and its label rectangle; the rectangle's angle is
+     * atan2(rotate_vector[1], rotate_vector[0]) with rotate_vector = R(q) [0, rand_y, 0] (peg_in_hole.py:58,65-72) */
+    if (entered && st == 2) S->grasp_ang = FN(det_atan2)(S->rand_y * Rp.m[1][1], S->rand_y * Rp.m[0][1]);
     v3 tp = FN(m3_v_add)(&Rp, FN(v3_make)(RC(0), S->rand_y, RC(0)), FN(v3_make)(S->ppos[0], S->ppos[1], S->ppos[2]));
     real qx = S->pquat[0], qy = S->pquat[1], qz = S->pquat[2], qw = S->pquat[3];
     real yaw = FN(det_atan2)(RC(2) * FMA(qx, qy, qw * qz), FMA(qw, qw, qx * qx) - FMA(qy, qy, qz * qz));

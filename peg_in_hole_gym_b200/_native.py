@@ -61,9 +61,10 @@ def lib():
     L.pih_ik_targets.argtypes = [vp, vp, vp, vp]
     L.pih_ee_pose.argtypes = [vp, vp, vp, vp]
     L.pih_render.argtypes = [vp, i32, i32, vp, vp]
+    L.pih_grasp_labels.argtypes = [vp, i32, i32, vp, vp, vp]
     L.pih_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     for name in ("pih_create", "pih_env_offset", "pih_reset", "pih_step", "pih_step_host", "pih_rollout",
-                 "pih_ik_targets", "pih_ee_pose", "pih_measure_fp32_peak", "pih_action_dim", "pih_render"):
+                 "pih_ik_targets", "pih_ee_pose", "pih_measure_fp32_peak", "pih_action_dim", "pih_render", "pih_grasp_labels"):
         getattr(L, name).restype = C.c_int
     if L.pih_abi_version() != 1:
         raise ImportError("libpih_b200.so ABI version mismatch")
@@ -73,7 +74,7 @@ def lib():
 
 EXPORTS = ["pih_abi_version", "pih_state_words", "pih_action_dim", "pih_obs_dim", "pih_create", "pih_destroy",
            "pih_last_error", "pih_env_offset", "pih_reset", "pih_step", "pih_step_host", "pih_rollout",
-           "pih_ik_targets", "pih_ee_pose", "pih_render", "pih_measure_fp32_peak"]
+           "pih_ik_targets", "pih_ee_pose", "pih_render", "pih_grasp_labels", "pih_measure_fp32_peak"]
 
 
 def make_config(num_envs, task="peg-in-hole", arm="panda", fly_object="banana", sub_num=None, env_id_base=0,

@@ -24,6 +24,7 @@
 #define PIH_S_FSM_T 22          /* int bits: engine steps already spent in cur_state (state_t / timeStep) */
 #define PIH_S_RANDY 23          /* random_vector[1] ~ U(-0.03, 0.03) */
 #define PIH_S_MTGT 40           /* 40..46 arm joint position targets that persist between FSM states */
+#define PIH_S_GRASP_ANG 47      /* grasp angle captured on entering FSM state 2 (peg_in_hole.py:65-72): labels of random_grasp */
 
 #define PIH_FLAG_DONE 1
 #define PIH_FLAG_SUCCESS 2
@@ -103,6 +104,10 @@
 
 /* camera of PegInHole.render (envs/peg_in_hole.py:276-304): eye at the end effector looking along -z, up +y,
  * FOV 60 deg, aspect 1, near 0.001, far 1000, 300 x 300; output channels (depth, r, g, b) */
+#define PIH_LABEL_LENGTH 0.1     /* peg_in_hole.py:73-74: half extents of the grasp rectangle in normalised image units */
+#define PIH_LABEL_WIDTH 0.2
+#define PIH_LABEL_POS_VALUE 50.0 /* peg_in_hole.py:87 */
+#define PIH_LABEL_NONE (-100.0)  /* grasp angle word before FSM state 2 has been entered: the label images are still empty */
 #define PIH_CAM_W 300
 #define PIH_CAM_H 300
 #define PIH_CAM_TAN_HALF_FOV 0.5773502691896257   /* tan(30 deg) */

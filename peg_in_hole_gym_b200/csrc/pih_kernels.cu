@@ -153,6 +153,7 @@ template <int ARM, int TASK> PIH_D void mailbox_put(float (*mb)[32], int lane, c
   mb[PIH_MB_FSM_STATE][lane] = __int_as_float(S.fsm_state); mb[PIH_MB_FSM_T][lane] = __int_as_float(S.fsm_t);
 #pragma unroll
   for (int k = 0; k < 7; ++k) mb[PIH_MB_MTGT + k][lane] = S.mtgt[k];
+  mb[PIH_MB_GRASP_ANG][lane] = S.grasp_ang;
 }
 
 template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(SimParams P, const float* __restrict__ action, float* __restrict__ obs,
@@ -745,6 +746,17 @@ int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, vo
 #undef RLAUNCH
   ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_render launch", ce);
+  return PIH_OK;
+}
+
+int pih_grasp_labels(pih_handle* h, int32_t width, int32_t height, float* labels_dev, float* params_dev, void* stream) {
+  if (!h || !labels_dev || width <= 0 || height <= 0) return PIH_ERR_INVALID;
+  if (!h->was_reset) return fail(h, PIH_ERR_STATE, "grasp_labels() before reset()", cudaSuccess);
+  if (use_device(h)) return PIH_ERR_CUDA;
+  dim3 grid((unsigned)((width * height + 256 * PIH_RENDER_PPT - 1) / (256 * PIH_RENDER_PPT)), (unsigned)h->P.n);
+  k_labels<<<grid, 256, 0, (cudaStream_t)stream>>>(h->P, (int)width, (int)height, labels_dev, params_dev);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_labels launch", ce);
   return PIH_OK;
 }
 

@@ -297,4 +297,65 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(256) k_render(Sim
 #undef IN_RECT
 }
 
+// ---------------------------------------------------------------- grasp label images of random_grasp
+// peg_in_hole.py:41-45,65-98: on entering FSM state 2 the reference fills a rotated rectangle (half extents 0.1 x 0.2 in
+// normalised image units, angle = atan2 of the rotated random_vector) into pos_img (50), ang_img and wid_img with
+// skimage.draw.polygon and returns [pos_img, sin(2 ang_img), cos(2 ang_img), wid_img] plus [x, y, angle in degrees,
+// width, length].  Vertices and inside test (closed quad, pixel = integer point) are shared with the oracle.
+struct LabelRect { float vx[4], vy[4], s2, c2, wid, len; bool any; };
+PIH_D LabelRect label_rect(float ang, int W, int H) {
+  LabelRect R;
+  R.any = ang > (float)(0.5 * PIH_LABEL_NONE);
+  float sa, ca;
+  det_sincos(R.any ? ang : 0.0f, sa, ca);
+  det_sincos(R.any ? 2.0f * ang : 0.0f, R.s2, R.c2);
+  const float L = (float)PIH_LABEL_LENGTH, Wd = (float)PIH_LABEL_WIDTH, S0 = (float)W, S1 = (float)H;
+  // a, c, b, d of peg_in_hole.py:78-83; first coordinate <-> image column, second <-> image row (pos_img[cc, rr])
+  R.vx[0] = (1.0f + L * ca + Wd * sa) / 2.0f * S0; R.vy[0] = (1.0f - L * sa + Wd * ca) / 2.0f * S1;
+  R.vx[1] = (1.0f - L * ca + Wd * sa) / 2.0f * S0; R.vy[1] = (1.0f + L * sa + Wd * ca) / 2.0f * S1;
+  R.vx[2] = (1.0f - L * ca - Wd * sa) / 2.0f * S0; R.vy[2] = (1.0f + L * sa - Wd * ca) / 2.0f * S1;
+  R.vx[3] = (1.0f + L * ca - Wd * sa) / 2.0f * S0; R.vy[3] = (1.0f - L * sa - Wd * ca) / 2.0f * S1;
+  float dx = R.vx[0] - R.vx[3], dy = R.vy[0] - R.vy[3];
+  R.wid = sqrtf(fmaf(dx, dx, dy * dy));
+  dx = R.vx[0] - R.vx[1]; dy = R.vy[0] - R.vy[1];
+  R.len = sqrtf(fmaf(dx, dx, dy * dy));
+  return R;
+}
+PIH_D bool label_inside(const LabelRect& R, float x, float y) {
+  bool pos = true, neg = true;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int m = (k + 1) & 3;
+    float cr = fmaf(R.vx[m] - R.vx[k], y - R.vy[k], -((R.vy[m] - R.vy[k]) * (x - R.vx[k])));
+    pos = pos && (cr >= 0.0f); neg = neg && (cr <= 0.0f);
+  }
+  return R.any && (pos || neg);
+}
+// labels float[n][4][H][W] (pos, sin, cos, wid); params float[n][5] (x, y, angle in degrees, width, length in pixels)
+__global__ void __launch_bounds__(256) k_labels(SimParams P, int W, int H, float* __restrict__ labels, float* __restrict__ params) {
+  const int e = blockIdx.y;
+  const float ang = reinterpret_cast<const float*>(&P.state[(size_t)(PIH_S_GRASP_ANG >> 2) * P.n + e])[PIH_S_GRASP_ANG & 3];
+  const LabelRect R = label_rect(ang, W, H);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && params) {
+    float* o = params + 5 * (size_t)e;
+    o[0] = 0.0f; o[1] = 0.0f;
+    o[2] = R.any ? ang / (float)3.141592653589793 * 180.0f : 0.0f;
+    o[3] = R.any ? R.wid : 0.0f; o[4] = R.any ? R.len : 0.0f;
+  }
+  const int npix = W * H;
+  const float invW = 1.0f / (float)W;
+  float* img = labels + (size_t)e * 4 * npix;
+#pragma unroll 1
+  for (int it = 0; it < PIH_RENDER_PPT; ++it) {
+    const int pix = (blockIdx.x * PIH_RENDER_PPT + it) * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const int row = (int)(((float)pix + 0.5f) * invW), col = pix - row * W;
+    const bool in = label_inside(R, (float)col, (float)row);
+    __stcs(&img[pix], in ? (float)PIH_LABEL_POS_VALUE : 0.0f);
+    __stcs(&img[npix + pix], in ? R.s2 : 0.0f);
+    __stcs(&img[2 * npix + pix], in ? R.c2 : 1.0f);
+    __stcs(&img[3 * npix + pix], in ? R.wid : 0.0f);
+  }
+}
+
 }  // namespace pih

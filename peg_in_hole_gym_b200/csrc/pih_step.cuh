@@ -329,6 +329,7 @@ template <int ARM, int TASK> PIH_D void reset_env(const SimParams& P, EnvState& 
   S.flags = 0;
   S.fsm_state = 0; S.fsm_t = 0;
   S.rand_y = fmaf(u[3], 0.06f, -0.03f);
+  S.grasp_ang = (float)PIH_LABEL_NONE;
 #pragma unroll
   for (int i = 0; i < 7; ++i) S.mtgt[i] = (i < ArmDims<ARM>::NARM) ? T.rest[i < ArmDims<ARM>::NARM ? i : 0] : 0.0f;
 }
@@ -364,13 +365,17 @@ template <int ARM, int TASK> PIH_D bool apply_action(const SimParams& P, EnvStat
     int lim = 0;
 #pragma unroll
     for (int k = 0; k < PIH_FSM_NSTATES; ++k) lim = (S.fsm_state == k) ? fsm_steps[k] : lim;
-    if (S.fsm_t == lim) {
+    const bool entered = (S.fsm_t == lim);
+    if (entered) {
       S.fsm_state += 1; S.fsm_t = 0;
       if (S.fsm_state >= PIH_FSM_NSTATES) S.fsm_state = 0;
     }
     S.fsm_t += 1;
     const int st = S.fsm_state;
     m3 Rp = quat_to_m3(S.pquat);
+    // entering state 2 the reference renders the grasp image and labels it with the rectangle whose angle is
+    // atan2 of R(q_peg) random_vector = rand_y * (second column of R) (peg_in_hole.py:58,65-72)
+    if (entered && st == 2) S.grasp_ang = det_atan2(S.rand_y * Rp.m[1][1], S.rand_y * Rp.m[0][1]);
     v3 tp = mv_add(Rp, mk(0.0f, S.rand_y, 0.0f), mk(S.ppos[0], S.ppos[1], S.ppos[2]));
     float qx = S.pquat[0], qy = S.pquat[1], qz = S.pquat[2], qw = S.pquat[3];
     float yaw = det_atan2(2.0f * fmaf(qx, qy, qw * qz), fmaf(qw, qw, qx * qx) - fmaf(qy, qy, qz * qz));
@@ -441,6 +446,7 @@ template <int ARM, int TASK> PIH_D bool apply_action(const SimParams& P, EnvStat
 #define PIH_MB_FSM_STATE 28
 #define PIH_MB_FSM_T 29
 #define PIH_MB_MTGT 30
+#define PIH_MB_GRASP_ANG 37
 
 // Everything of one env.step after apply_action: stepSimulation (ABA, M^-1, contacts, PGS, integration) and get_info.
 // The body lives in pih_step_body.inc and is instantiated twice: the classic single-warp order and the warp-specialised

@@ -37,7 +37,8 @@ class PegInHoleScripted(PegInHole):
     """The task exactly as the reference ships it (peg_in_hole.py:30-37): ``apply_action`` is a no-op and one
     ``step()`` runs the whole scripted grasp -> lift -> insert -> release episode (10 timed states, 2226 engine
     steps of 1/240 s) and returns the success reward of peg_in_hole.py:114-117.  The state machine runs inside the
-    rollout kernel; the observation is the 5-vector (the camera image of peg_in_hole.py:66-98 is SURVEY 8f rank 3).
+    rollout kernel; the observation is the 5-vector; the camera image and the grasp label images of peg_in_hole.py:66-98
+    come from ``render()`` and ``random_grasp_labels()``.
     Differences flagged NEW: rigid peg segment instead of the 25-link pipe; the JOINT_GEAR grasp constraint
     (peg_in_hole.py:99-104) is replaced by the friction grasp alone."""
     native_task = "peg-in-hole-scripted"
@@ -51,3 +52,9 @@ class PegInHoleScripted(PegInHole):
 
     def native_step(self, action):       # get_info -> random_grasp(): `while not done` loop (peg_in_hole.py:52-112)
         self.p.rollout(self.EPISODE_STEPS, count=False)
+
+    def random_grasp_labels(self, width=300, height=300):
+        """What the reference's ``random_grasp`` returns beside the reward (peg_in_hole.py:119):
+        ``[[pos_img, sin_img, cos_img, wid_img], [x, y, angle_deg, width, length]]`` for every env, as tensors
+        ``labels[N, 4, H, W]`` and ``params[N, 5]`` (the rectangle was captured when the state machine entered state 2)."""
+        return self.p.grasp_labels(width, height)

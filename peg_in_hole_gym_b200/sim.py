@@ -143,6 +143,15 @@ class BatchedSim:
         N.check(self._L.pih_render(self._h, int(width), int(height), out.data_ptr(), self._stream()), self._h, "pih_render")
         return out
 
+    def grasp_labels(self, width=300, height=300):
+        """Label images of the shipped task's random_grasp (peg_in_hole.py:41-45,65-98): ``(labels[N, 4, H, W], params[N, 5])``
+        = ([pos_img, sin_img, cos_img, wid_img], [x, y, angle in degrees, width, length])."""
+        labels = torch.empty(self.n, 4, height, width, dtype=torch.float32, device=self.device)
+        params = torch.empty(self.n, 5, dtype=torch.float32, device=self.device)
+        N.check(self._L.pih_grasp_labels(self._h, int(width), int(height), labels.data_ptr(), params.data_ptr(), self._stream()),
+                self._h, "pih_grasp_labels")
+        return labels, params
+
     # -- state views (SoA words -> [N, k]); copies, for tests / checkpointing
     def words(self, first, count=1):
         flat = self.state.permute(1, 0, 2).reshape(self.n, -1)

@@ -75,6 +75,7 @@ def lib():
         L.pih_oracle_rng4.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.pih_oracle_philox.argtypes = [C.c_void_p] * 3
         L.pih_oracle_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.pih_oracle_grasp_labels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -85,7 +86,7 @@ def _p(a):
 
 STATE_WORDS = 48
 S_Q, S_STEP, S_EPISODE, S_FLAGS, S_QD, S_PPOS, S_PQUAT, S_PVEL, S_PANG = 0, 9, 10, 11, 12, 24, 27, 32, 35
-S_FSM_STATE, S_FSM_T, S_RANDY, S_MTGT = 21, 22, 23, 40
+S_FSM_STATE, S_FSM_T, S_RANDY, S_MTGT, S_GRASP_ANG = 21, 22, 23, 40, 47
 
 
 class Oracle:
@@ -131,6 +132,13 @@ class Oracle:
         img = np.zeros((hi - lo, height, width, 4), np.float32)
         lib().pih_oracle_render(self.h, width, height, lo, hi, _p(img))
         return img
+
+    def grasp_labels(self, width=300, height=300, lo=0, hi=None):
+        hi = self.n if hi is None else hi
+        lab = np.zeros((hi - lo, 4, height, width), np.float32)
+        par = np.zeros((hi - lo, 5), np.float32)
+        lib().pih_oracle_grasp_labels(self.h, width, height, lo, hi, _p(lab), _p(par))
+        return lab, par
 
     def get_state(self):
         w = np.zeros((STATE_WORDS // 4, self.n, 4), np.float32)

@@ -275,6 +275,38 @@ def test_zero_copy_host_path_with_frozen_envs_and_fresh_buffers(monkeypatch, ws)
     _assert_state_equal(sim, orc)
 
 
+def test_grasp_label_images_match_oracle():
+    """SURVEY 8f rank 3, second half: the label images of random_grasp (peg_in_hole.py:65-98) - CUDA == oracle, exactly,
+    before the capture, after it, and for hand-set angles on a non-square image."""
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    n = 40
+    sim = BatchedSim(n, task="peg-in-hole-scripted", offset=(2.0, 3.0, 0.0), seed=3, device=0)
+    orc = ol.Oracle(ol.make_config(n, task=2, offset=(2.0, 3.0, 0.0), seed=3))
+    sim.reset(); orc.reset()
+    for steps in (0, 545, 700):
+        if steps:
+            sim.rollout(steps); orc.rollout(steps)
+        gl, gp = sim.grasp_labels(300, 300)
+        cl, cp = orc.grasp_labels(300, 300)
+        assert np.array_equal(gl.cpu().numpy(), cl) and np.array_equal(gp.cpu().numpy(), cp), steps
+    _assert_state_equal(sim, orc)
+    w = orc.get_state()
+    flat = np.ascontiguousarray(w.transpose(1, 0, 2)).reshape(n, -1)
+    flat[:, ol.S_GRASP_ANG] = np.linspace(-3.1, 3.1, n).astype(np.float32)
+    w2 = np.ascontiguousarray(flat.reshape(n, -1, 4).transpose(1, 0, 2))
+    orc.set_state(w2); sim.state.copy_(torch.from_numpy(w2))
+    gl, gp = sim.grasp_labels(80, 64)
+    cl, cp = orc.grasp_labels(80, 64)
+    assert np.array_equal(gl.cpu().numpy(), cl) and np.array_equal(gp.cpu().numpy(), cp)
+    import peg_in_hole_gym_b200 as gym
+    env = gym.make('peg-in-hole-mp-v0', client=gym.DIRECT, task='peg-in-hole-scripted', mp_num=1, sub_num=4, offset=[2., 3., 0.], shard=False)
+    env.reset()
+    env.step(env.action_space.sample_array())
+    labels, params = env.plugin.random_grasp_labels()
+    assert tuple(labels.shape) == (4, 4, 300, 300) and tuple(params.shape) == (4, 5) and bool((labels[:, 0] == 50).any())
+    env.close()
+
+
 def test_fp32_gpu_vs_fp64_oracle_drift_within_tolerance():
     """north_star tolerance: <=1e-3 m / 1e-2 rad per step; drift over the 200-step horizon is reported."""
     n = 128

@@ -244,3 +244,42 @@ def test_ur5_holds_its_pose_and_fly_object_is_ballistic():
     want = p0 + v0 * dt * k
     want[:, 2] -= 9.8 * dt * dt * k * (k + 1) / 2
     assert np.abs(ol.state_field(o.get_state(), ol.S_PPOS, 3) - want).max() < 1e-6
+
+
+def test_grasp_label_images_follow_random_grasp():
+    """peg_in_hole.py:41-45,65-98: empty labels (cos image = 1) until the state machine enters state 2; then a rotated
+    rectangle of 0.1 x 0.2 normalised half extents = 30 x 60 pixels on 300 x 300, angle = atan2 of the rotated
+    random_vector (the peg still lies along its spawn axis: +-90 degrees), pos 50, sin/cos of twice the angle, width."""
+    n = 6
+    o = ol.Oracle(ol.make_config(n, task=2, offset=(2.0, 3.0, 0.0), seed=3))
+    o.reset()
+    lab, par = o.grasp_labels(300, 300)
+    assert not lab[:, [0, 1, 3]].any() and (lab[:, 2] == 1.0).all() and not par.any()
+    o.rollout(540)                                               # states 0, 1 last 60 + 480 engine steps
+    assert (ol.state_int(o.get_state(), ol.S_FSM_STATE) == 1).all()
+    assert (ol.state_field(o.get_state(), ol.S_GRASP_ANG)[:, 0] == -100.0).all()
+    o.rollout(2)
+    assert (ol.state_int(o.get_state(), ol.S_FSM_STATE) == 2).all()
+    lab, par = o.grasp_labels(300, 300)
+    ang = ol.state_field(o.get_state(), ol.S_GRASP_ANG)[:, 0]
+    ry = ol.state_field(o.get_state(), ol.S_RANDY)[:, 0]
+    assert np.allclose(np.abs(ang), np.pi / 2, atol=2e-2) and (np.sign(ang) == np.sign(ry)).all()
+    assert np.allclose(par[:, 2], ang / np.pi * 180, atol=1e-3) and np.allclose(par[:, 3], 60, atol=1e-3) and np.allclose(par[:, 4], 30, atol=1e-3)
+    inside = lab[:, 0] == 50.0
+    assert ((lab[:, 0] == 0.0) | inside).all()
+    area = inside.sum(axis=(1, 2))
+    assert ((area >= 1700) & (area <= 1950)).all(), area          # 60 x 30 rectangle, closed boundary
+    assert inside[:, 150, 150].all() and not inside[:, 10, 10].any()
+    for i in range(n):
+        assert np.allclose(lab[i, 1][inside[i]], np.sin(2 * ang[i]), atol=1e-5) and not lab[i, 1][~inside[i]].any()
+        assert np.allclose(lab[i, 2][inside[i]], np.cos(2 * ang[i]), atol=1e-5) and (lab[i, 2][~inside[i]] == 1.0).all()
+        assert np.allclose(lab[i, 3][inside[i]], 60, atol=1e-3) and not lab[i, 3][~inside[i]].any()
+    # a non-square image and a rotated rectangle: symmetric about the centre, rows <-> second vertex coordinate
+    w = o.get_state()
+    flat = np.ascontiguousarray(w.transpose(1, 0, 2)).reshape(n, -1)
+    flat[:, ol.S_GRASP_ANG] = np.linspace(-3.0, 3.0, n)
+    o.set_state(flat.reshape(n, -1, 4).transpose(1, 0, 2))
+    lab, par = o.grasp_labels(80, 64)
+    ins = lab[:, 0] == 50.0
+    assert ins.any(axis=(1, 2)).all()
+    assert (ins[:, 1:, 1:] == ins[:, 1:, 1:][:, ::-1, ::-1]).mean() > 0.98   # point symmetry about (W/2, H/2)
