@@ -154,7 +154,9 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--arm", default="panda")
     ap.add_argument("--task", default="peg-in-hole")
-    ap.add_argument("--gather", action="store_true", help="all ranks send packed (obs,reward,done) rows to rank 0 every step (NCCL)")
+    ap.add_argument("--gather", nargs="?", const="nccl", default=None, choices=["nccl", "peer"],
+                    help="every step all ranks deliver their (obs,reward,done) rows to rank 0: 'nccl' = pack + gather collective; "
+                         "'peer' = the step kernel stores them into rank 0's buffer over NVLink peer memory and signals a flag")
     ap.add_argument("--l2", choices=["rotate", "flush"], default="rotate",
                     help="rotate: inputs larger than L2 (many independent batches round-robin); flush: one batch, L2 flushed between steps")
     ap.add_argument("--no-cpu", action="store_true")
@@ -167,7 +169,7 @@ def main():
     import torch.distributed as dist
     from peg_in_hole_gym_b200 import _native
     from peg_in_hole_gym_b200.sim import BatchedSim
-    from peg_in_hole_gym_b200.parallel import gather_rows_to_rank0, pack_rows
+    from peg_in_hole_gym_b200.parallel import PeerLearnerBuffer, gather_rows_to_rank0, pack_rows
 
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -214,6 +216,8 @@ def main():
         if L.pih_measure_fp32_peak(local, C.byref(v)) == 0:
             peak_tf = v.value
 
+    peer = PeerLearnerBuffer(sims[0]) if (args.gather == "peer" and world > 1) else None
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -226,9 +230,15 @@ def main():
             flush.zero_()
         if timed is not None:
             timed[0].record()
-        sm.step(ring[((i // nb_batches) * 7 + b * 13) % n_act])
-        if args.gather and world > 1:
-            gather_rows_to_rank0(pack_rows(sm.obs, sm.reward, sm.done.float()), counts=[n] * world)
+        a = ring[((i // nb_batches) * 7 + b * 13) % n_act]
+        if peer is not None:
+            peer.step(a, sm)              # outputs go straight into rank 0's learner buffer, then the flag
+            if rank == 0:
+                peer.wait()
+        else:
+            sm.step(a)
+            if args.gather == "nccl" and world > 1:
+                gather_rows_to_rank0(pack_rows(sm.obs, sm.reward, sm.done.float()), counts=[n] * world)
         if timed is not None:
             timed[1].record()
 
@@ -256,6 +266,8 @@ def main():
         barrier()
         t_wall = time.perf_counter() - t_wall0
         dev_ms = ev0.elapsed_time(ev1)
+    if peer is not None and rank == 0:
+        peer.check()      # no device-side wait may have timed out
     clocks = sampler.stop() if sampler else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # single-launch rollout (in-kernel Philox actions); first launch of the kernel is a warm-up (local-memory resize)
@@ -327,7 +339,7 @@ def main():
                        "l2": (f"inputs larger than L2: {nb_batches} independent {n}-env batches ({nb_batches * bytes_per_batch / 1e6:.0f} MB of state+actions+outputs) "
                               "visited round-robin, phases of the 200-step episode spread evenly; K launches inside one CUDA-event pair"
                               if args.l2 == "rotate" else "flushed between timed steps (256 MiB memset); per-step CUDA events summed"),
-                       "gather_to_rank0": bool(args.gather), "parallelism": f"env-sharded x{world}, no data-path collective"},
+                       "gather_to_rank0": args.gather or False, "parallelism": f"env-sharded x{world}, no data-path collective"},
             "e2e": {"value": total_envs * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * adim * 4,
                     "d2h_bytes_per_step": n * (20 + 4 + 1), "steps": e2e_steps, "timing": "wall clock per step: pih_step_host on page-locked host buffers = one launch whose SMs read that step's actions from host memory and write obs|reward|done back to host memory over PCIe (zero-copy), stream sync, host reads the result; a fresh i.i.d. host action batch every step"},
             "gpu_launches": args.steps,

@@ -112,6 +112,25 @@ int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, vo
  * Before state 2 has been entered the images are the reference's initial ones (zeros, cos = 1). */
 int pih_grasp_labels(pih_handle* h, int32_t width, int32_t height, float* labels_dev, float* params_dev, void* stream);
 
+/* Gather to a rank-0 learner buffer WITHOUT a collective (preferred form).  The reference gathers the
+ * workers' results through multiprocessing queues (base_env_mp.py:44-50).  Here every rank hands pih_step output
+ * pointers that are PEER mappings of its slice of rank 0's buffer, so the step kernel itself stores the rows over
+ * NVLink; pih_signal_flag then publishes `value` (the step number) in the rank's flag word inside that buffer
+ * (stream-ordered after the step, fenced system-wide), and rank 0 enqueues pih_wait_flags, which returns control to
+ * its stream once all `count` flags have reached `value`.  A wait that exceeds timeout_ms writes 1 + the index of the
+ * late flag to *timed_out_dev and gives up (no unbounded device-side spin). */
+/* pih_step whose kernel also publishes flag_value in *flag_dev once all its rows have been stored (fused epilogue;
+ * for batches that run the classic kernels a one-thread signalling kernel follows instead). */
+int pih_step_signal(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint32_t* flag_dev,
+                    uint32_t flag_value, void* stream);
+int pih_peer_alloc(int32_t device, uint64_t bytes, void** ptr_out, uint8_t handle_out[64]);  /* owner: zeroed buffer + its IPC handle */
+int pih_peer_open(int32_t device, const uint8_t handle[64], void** ptr_out);   /* other rank: map it on ITS device (peer memory) */
+int pih_peer_release(void* ptr, int32_t is_owner);
+int pih_enable_peer(pih_handle* h, int32_t peer_device);   /* same process, two devices: let this handle's kernels address peer_device */
+int pih_signal_flag(pih_handle* h, uint32_t* flag_dev, uint32_t value, void* stream);
+int pih_wait_flags(pih_handle* h, const uint32_t* flags_dev, int32_t count, uint32_t value, uint32_t timeout_ms,
+                   uint32_t* timed_out_dev, void* stream);
+
 /* FP32 FMA-throughput micro-benchmark (roofline denominator): returns measured TFLOP/s. */
 int pih_measure_fp32_peak(int device, double* tflops_out);
 

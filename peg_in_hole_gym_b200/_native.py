@@ -62,9 +62,17 @@ def lib():
     L.pih_ee_pose.argtypes = [vp, vp, vp, vp]
     L.pih_render.argtypes = [vp, i32, i32, vp, vp]
     L.pih_grasp_labels.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.pih_step_signal.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint32, vp]
+    L.pih_peer_alloc.argtypes = [i32, C.c_uint64, C.POINTER(vp), C.c_char_p]
+    L.pih_peer_open.argtypes = [i32, C.c_char_p, C.POINTER(vp)]
+    L.pih_peer_release.argtypes = [vp, i32]
+    L.pih_enable_peer.argtypes = [vp, i32]
+    L.pih_signal_flag.argtypes = [vp, vp, C.c_uint32, vp]
+    L.pih_wait_flags.argtypes = [vp, vp, i32, C.c_uint32, C.c_uint32, vp, vp]
     L.pih_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     for name in ("pih_create", "pih_env_offset", "pih_reset", "pih_step", "pih_step_host", "pih_rollout",
-                 "pih_ik_targets", "pih_ee_pose", "pih_measure_fp32_peak", "pih_action_dim", "pih_render", "pih_grasp_labels"):
+                 "pih_ik_targets", "pih_ee_pose", "pih_measure_fp32_peak", "pih_action_dim", "pih_render", "pih_grasp_labels",
+                 "pih_step_signal", "pih_peer_alloc", "pih_peer_open", "pih_peer_release", "pih_enable_peer", "pih_signal_flag", "pih_wait_flags"):
         getattr(L, name).restype = C.c_int
     if L.pih_abi_version() != 1:
         raise ImportError("libpih_b200.so ABI version mismatch")
@@ -74,7 +82,9 @@ def lib():
 
 EXPORTS = ["pih_abi_version", "pih_state_words", "pih_action_dim", "pih_obs_dim", "pih_create", "pih_destroy",
            "pih_last_error", "pih_env_offset", "pih_reset", "pih_step", "pih_step_host", "pih_rollout",
-           "pih_ik_targets", "pih_ee_pose", "pih_render", "pih_grasp_labels", "pih_measure_fp32_peak"]
+           "pih_ik_targets", "pih_ee_pose", "pih_render", "pih_grasp_labels", "pih_step_signal", "pih_peer_alloc", "pih_peer_open", "pih_peer_release",
+           "pih_enable_peer", "pih_signal_flag",
+           "pih_wait_flags", "pih_measure_fp32_peak"]
 
 
 def make_config(num_envs, task="peg-in-hole", arm="panda", fly_object="banana", sub_num=None, env_id_base=0,

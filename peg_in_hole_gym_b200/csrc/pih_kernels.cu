@@ -156,8 +156,11 @@ template <int ARM, int TASK> PIH_D void mailbox_put(float (*mb)[32], int lane, c
   mb[PIH_MB_GRASP_ANG][lane] = S.grasp_ang;
 }
 
+struct StepSignal { unsigned* flag; unsigned value; unsigned* cta_counter; };   // fused "rows delivered" signal (nullable flag)
+
 template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(SimParams P, const float* __restrict__ action, float* __restrict__ obs,
-                                                                          float* __restrict__ reward, unsigned char* __restrict__ done) {
+                                                                          float* __restrict__ reward, unsigned char* __restrict__ done,
+                                                                          StepSignal sig) {
   __shared__ float mb[PIH_MB_WORDS][32];
   constexpr int A = ArmDims<ARM>::ADIM, nb = ArmDims<ARM>::NB;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -204,9 +207,24 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(
       if (idx < 5 * rows) obs[(size_t)blockIdx.x * 160 + idx] = so[idx];
     }
   }
-  if (e >= P.n) return;
-  if (reward) reward[e] = r;
-  if (done) done[e] = d;
+  if (e < P.n) {
+    if (reward) reward[e] = r;
+    if (done) done[e] = d;
+  }
+  if (sig.flag) {
+    // Fused gather epilogue: the output pointers may be peer mappings of a learner buffer on another
+    // GPU.  Every CTA makes its rows visible system-wide and counts itself; the last one publishes the step number in
+    // this rank's flag word (and re-arms the counter), so no separate signalling launch follows the step.
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+      if (atomicAdd(sig.cta_counter, 1u) == gridDim.x - 1) {
+        *sig.cta_counter = 0u;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned*>(sig.flag) = sig.value;
+      }
+    }
+  }
 }
 
 template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_rollout_ws(SimParams P, int steps, float* __restrict__ obs, float* __restrict__ reward,
@@ -310,6 +328,30 @@ template <int ARM> __global__ void __launch_bounds__(128) k_ee(SimParams P, floa
   }
 }
 
+// ---- gather-to-learner without a collective: every rank's step kernel stores its (obs, reward, done) rows straight
+// into rank 0's buffer through a peer mapping (NVLink); a one-thread kernel then publishes the step number in that rank's
+// flag, and rank 0 waits on the flags in its own stream.  The stores of the step kernel are complete before the
+// signal kernel starts (stream order); the fences order the flag against them across devices.
+__global__ void k_signal_flag(volatile unsigned* flag, unsigned value) {
+  __threadfence_system();
+  *flag = value;
+  __threadfence_system();
+}
+// waits until every flag has reached `value` (steps count up, so >=); gives up after `timeout_ns` and records it
+__global__ void k_wait_flags(const volatile unsigned* flags, int count, unsigned value, unsigned long long timeout_ns, unsigned* timed_out) {
+  const int i = threadIdx.x;
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  if (i < count) {
+    while ((int)(flags[i] - value) < 0) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > timeout_ns) { atomicExch(timed_out, 1u + (unsigned)i); break; }
+      __nanosleep(200);
+    }
+  }
+  __threadfence_system();
+}
+
 __global__ void k_init_state(float4* state, int n) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
@@ -356,6 +398,7 @@ struct pih_handle {
   const void* alias_host[PIH_ALIAS_SLOTS];
   void* alias_dev[PIH_ALIAS_SLOTS];
   int n_alias, alias_next, no_zero_copy;
+  unsigned* d_cta_counter;   // fused step signal: CTAs that have delivered their rows (re-armed by the last one)
 };
 
 static int g_tables_device = -1;
@@ -516,6 +559,8 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   if (bs) { int b = atoi(bs); if (b == 32 || b == 64 || b == 128) h->block = b; }
   k_init_state<<<(P.n + 127) / 128, 128>>>(P.state, P.n);
   cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess) ce = cudaMalloc(&h->d_cta_counter, sizeof(unsigned));
+  if (ce == cudaSuccess) ce = cudaMemset(h->d_cta_counter, 0, sizeof(unsigned));
   if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
   if (ce != cudaSuccess) { delete h; return PIH_ERR_CUDA; }
   *out = h;
@@ -524,6 +569,7 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
 
 void pih_destroy(pih_handle* h) {
   if (!h) return;
+  if (h->d_cta_counter) cudaFree(h->d_cta_counter);
   if (h->h_action) cudaFreeHost(h->h_action);
   if (h->h_obs) cudaFreeHost(h->h_obs);     // one pinned block: obs | reward | done
   if (h->d_action) cudaFree(h->d_action);
@@ -595,13 +641,31 @@ int pih_reset(pih_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stre
   return PIH_OK;
 }
 
+static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint32_t* flag_dev,
+                     uint32_t flag_value, void* stream);
+
 int pih_step(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream) {
+  return step_impl(h, action_dev, obs_dev, reward_dev, done_dev, nullptr, 0u, stream);
+}
+
+int pih_step_signal(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint32_t* flag_dev,
+                    uint32_t flag_value, void* stream) {
+  if (!flag_dev) return PIH_ERR_INVALID;
+  return step_impl(h, action_dev, obs_dev, reward_dev, done_dev, flag_dev, flag_value, stream);
+}
+
+static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint32_t* flag_dev,
+                     uint32_t flag_value, void* stream) {
   if (!h || !action_dev) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "step() before reset()", cudaSuccess);
   if ((uintptr_t)action_dev & (h->P.arm == PIH_ARM_PANDA ? 15 : 7)) return fail(h, PIH_ERR_INVALID, "action rows must be 16-byte (Box(4)) / 8-byte (Box(6)) aligned", cudaSuccess);
   if (use_device(h)) return PIH_ERR_CUDA;
-  if (h->ws) { LAUNCH_WS(k_step_ws, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev); }
-  else { LAUNCH(k_step, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev); }
+  const StepSignal sig = {flag_dev, flag_value, h->d_cta_counter};
+  if (h->ws) { LAUNCH_WS(k_step_ws, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev, sig); }
+  else {
+    LAUNCH(k_step, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev);
+    if (flag_dev) k_signal_flag<<<1, 1, 0, (cudaStream_t)stream>>>(flag_dev, flag_value);   // large batches: the extra launch is noise
+  }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_step launch", ce);
   h->P.global_step += 1;
@@ -747,6 +811,66 @@ int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, vo
   ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_render launch", ce);
   return PIH_OK;
+}
+
+// learner buffer shared between the rank processes of one node: allocated by its owner with cudaMalloc (a whole
+// allocation, so that its IPC handle maps exactly this buffer) and opened by every other rank ON THAT RANK'S OWN device,
+// which maps the owner's HBM into the opener's address space as peer memory (NVLink)
+int pih_peer_alloc(int32_t device, uint64_t bytes, void** ptr_out, uint8_t handle_out[64]) {
+  if (!ptr_out || !handle_out || bytes == 0) return PIH_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hd;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(ptr_out, (size_t)bytes) != cudaSuccess ||
+      cudaMemset(*ptr_out, 0, (size_t)bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+      cudaIpcGetMemHandle(&hd, *ptr_out) != cudaSuccess) { cudaGetLastError(); return PIH_ERR_CUDA; }
+  memcpy(handle_out, &hd, 64);
+  return PIH_OK;
+}
+int pih_peer_open(int32_t device, const uint8_t handle[64], void** ptr_out) {
+  if (!ptr_out || !handle) return PIH_ERR_INVALID;
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, 64);
+  if (cudaSetDevice(device) != cudaSuccess || cudaIpcOpenMemHandle(ptr_out, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    cudaGetLastError();
+    return PIH_ERR_CUDA;
+  }
+  return PIH_OK;
+}
+int pih_peer_release(void* ptr, int32_t is_owner) {
+  if (!ptr) return PIH_OK;
+  cudaError_t ce = is_owner ? cudaFree(ptr) : cudaIpcCloseMemHandle(ptr);
+  if (ce != cudaSuccess) { cudaGetLastError(); return PIH_ERR_CUDA; }
+  return PIH_OK;
+}
+
+int pih_enable_peer(pih_handle* h, int32_t peer_device) {
+  if (!h) return PIH_ERR_INVALID;
+  if (peer_device == h->cfg.device) return PIH_OK;
+  if (use_device(h)) return PIH_ERR_CUDA;
+  int can = 0;
+  cudaError_t ce = cudaDeviceCanAccessPeer(&can, h->cfg.device, peer_device);
+  if (ce != cudaSuccess || !can) return fail(h, PIH_ERR_CUDA, "no peer access to that device", ce);
+  ce = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (ce == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); ce = cudaSuccess; }
+  return ce == cudaSuccess ? PIH_OK : fail(h, PIH_ERR_CUDA, "cudaDeviceEnablePeerAccess", ce);
+}
+
+int pih_signal_flag(pih_handle* h, uint32_t* flag_dev, uint32_t value, void* stream) {
+  if (!h || !flag_dev) return PIH_ERR_INVALID;
+  if (use_device(h)) return PIH_ERR_CUDA;
+  k_signal_flag<<<1, 1, 0, (cudaStream_t)stream>>>(flag_dev, value);
+  cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? PIH_OK : fail(h, PIH_ERR_CUDA, "k_signal_flag launch", ce);
+}
+
+int pih_wait_flags(pih_handle* h, const uint32_t* flags_dev, int32_t count, uint32_t value, uint32_t timeout_ms, uint32_t* timed_out_dev,
+                   void* stream) {
+  if (!h || !flags_dev || !timed_out_dev || count <= 0 || count > 1024) return PIH_ERR_INVALID;
+  if (use_device(h)) return PIH_ERR_CUDA;
+  k_wait_flags<<<1, ((count + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(flags_dev, (int)count, value, (unsigned long long)timeout_ms * 1000000ull,
+                                                                        timed_out_dev);
+  cudaError_t ce = cudaGetLastError();
+  return ce == cudaSuccess ? PIH_OK : fail(h, PIH_ERR_CUDA, "k_wait_flags launch", ce);
 }
 
 int pih_grasp_labels(pih_handle* h, int32_t width, int32_t height, float* labels_dev, float* params_dev, void* stream) {

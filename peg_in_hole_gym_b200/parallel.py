@@ -63,3 +63,120 @@ def gather_rows_to_rank0(rows, counts=None):
     if rank != 0:
         return None
     return torch.cat([b[:n] for b, n in zip(buf, counts)], 0)
+
+
+class _DevMem:
+    """Raw device allocation exposed to torch through __cuda_array_interface__ (zero-copy view, no ownership)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerLearnerBuffer:
+    """Gather to a rank-0 learner buffer WITHOUT a collective (preferred form).
+
+    Rank 0 owns one device allocation ``[world][obs n*5 f32 | reward n f32 | done n u8]`` plus one flag word per rank.
+    Every other rank opens its CUDA IPC handle ON ITS OWN GPU, which maps rank 0's HBM into that rank's address space as
+    peer memory (NVLink / NVSwitch), and hands its slice to ``pih_step`` as the output pointers: the step kernel itself
+    stores the rows into rank 0's HBM.  ``pih_signal_flag`` then publishes the step number, and rank 0's ``wait`` (a
+    bounded device-side wait in its own stream) returns the views of all ranks' rows.  Nothing is packed, copied or
+    reduced, and no host synchronisation is involved.  (There is no back-pressure: a learner that reads asynchronously
+    should alternate two buffers.)
+
+    ``rank`` / ``world_size`` / ``buf`` may be given explicitly to build several members inside ONE process on one GPU
+    (used by the single-GPU test); by default they come from torch.distributed and the buffer is shared over IPC."""
+
+    ALIGN = 256
+
+    def __init__(self, sim, rank=None, world_size=None, buf=None):
+        import ctypes as C
+        from . import _native as N
+        self.sim = sim
+        r, ws = world()
+        self.rank = r if rank is None else int(rank)
+        self.world_size = ws if world_size is None else int(world_size)
+        n, od = sim.n, sim.obs_dim
+        self.n, self.obs_dim = n, od
+        raw = n * od * 4 + n * 4 + n
+        self.per = (raw + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.flag_off = self.world_size * self.per
+        total = self.flag_off + self.ALIGN
+        self._raw, self._owner = None, False
+        if buf is not None:                                   # members of one process share a torch tensor
+            self.buf, self.base = buf, buf.data_ptr()
+            if buf.numel() < total:
+                raise ValueError("learner buffer too small")
+        else:
+            import torch.distributed as dist
+            L = sim._L
+            ptr, handle = C.c_void_p(), C.create_string_buffer(64)
+            if self.rank == 0:
+                N.check(L.pih_peer_alloc(sim.device.index, total, C.byref(ptr), handle), None, "pih_peer_alloc")
+                self._owner = True
+            obj = [handle.raw if self.rank == 0 else None]
+            if self.world_size > 1:
+                dist.broadcast_object_list(obj, src=0)
+                if self.rank != 0:
+                    N.check(L.pih_peer_open(sim.device.index, obj[0], C.byref(ptr)), None, "pih_peer_open")
+            self._raw = self.base = int(ptr.value)
+            # torch views exist on the owner only (the other ranks need nothing but the addresses)
+            self.buf = torch.as_tensor(_DevMem(self.base, total), device=sim.device) if self.rank == 0 else None
+            if self.world_size > 1:
+                dist.barrier()
+        self.timed_out = torch.zeros(1, dtype=torch.int32, device=sim.device)
+        self.step_no = 0
+
+    def close(self):
+        if self._raw:
+            self.buf = None
+            torch.cuda.synchronize(self.sim.device)
+            self.sim._L.pih_peer_release(self._raw, int(self._owner))
+            self._raw = None
+
+    @staticmethod
+    def total_bytes(n, obs_dim, world_size):
+        raw = n * obs_dim * 4 + n * 4 + n
+        per = (raw + PeerLearnerBuffer.ALIGN - 1) // PeerLearnerBuffer.ALIGN * PeerLearnerBuffer.ALIGN
+        return world_size * per + PeerLearnerBuffer.ALIGN
+
+    def _views(self, r):
+        n, od = self.n, self.obs_dim
+        base = self.buf[r * self.per:(r + 1) * self.per]
+        obs = base[:n * od * 4].view(torch.float32).view(n, od)
+        rew = base[n * od * 4:n * od * 4 + n * 4].view(torch.float32)
+        done = base[n * od * 4 + n * 4:n * od * 4 + n * 4 + n]
+        return obs, rew, done
+
+    def _ptrs(self, r):
+        n, od = self.n, self.obs_dim
+        b = self.base + r * self.per
+        return b, b + n * od * 4, b + n * od * 4 + n * 4
+
+    def _flag_ptr(self, r):
+        return self.base + self.flag_off + 4 * r
+
+    def step(self, action, sim=None):
+        """pih_step_signal: this rank's slice of the learner buffer as the outputs; the kernel publishes the step number.
+        ``sim``: another BatchedSim of the same size on this rank (several env batches may feed one learner buffer)."""
+        from . import _native as N
+        sim = self.sim if sim is None else sim
+        po, pr, pd = self._ptrs(self.rank)
+        self.step_no += 1
+        st = sim._stream()
+        N.check(sim._L.pih_step_signal(sim._h, action.data_ptr(), po, pr, pd, self._flag_ptr(self.rank), self.step_no, st), sim._h,
+                "pih_step_signal")
+
+    def wait(self, timeout_ms=2000):
+        """Rank 0: enqueue the wait for every rank's flag of the current step; returns [(obs, reward, done)] per rank
+        (views of the learner buffer, valid for work enqueued after this call on the same stream)."""
+        from . import _native as N
+        sim = self.sim
+        N.check(sim._L.pih_wait_flags(sim._h, self.base + self.flag_off, self.world_size, self.step_no, int(timeout_ms),
+                                      self.timed_out.data_ptr(), sim._stream()), sim._h, "pih_wait_flags")
+        return [self._views(r) for r in range(self.world_size)]
+
+    def check(self):
+        """Host-side: raises if a device-side wait gave up (synchronises the stream)."""
+        v = int(self.timed_out.item())
+        if v:
+            raise RuntimeError(f"peer gather: rank {v - 1} did not publish step {self.step_no} in time")

@@ -307,6 +307,40 @@ def test_grasp_label_images_match_oracle():
     env.close()
 
 
+def test_peer_write_gather_on_one_gpu_matches_plain_outputs():
+    """SURVEY 8e preferred form: the step kernel writes its rows into the learner buffer itself and publishes a flag;
+    the owner waits on the flags on the device.  Exercised here with two members inside one process on one GPU (across
+    processes the buffer is mapped through CUDA IPC; bench.py --gather peer runs that on >= 2 GPUs)."""
+    from peg_in_hole_gym_b200.parallel import PeerLearnerBuffer
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    n = 160
+    kw = dict(offset=(2.0, 3.0, 0.0), max_steps=12, auto_reset=True, seed=9, sub_num=2 * n)
+    sims = [BatchedSim(n, env_id_base=r * n, device=0, **kw) for r in range(2)]
+    refs = [BatchedSim(n, env_id_base=r * n, device=0, **kw) for r in range(2)]
+    for s_ in sims + refs:
+        s_.reset()
+    buf = torch.zeros(PeerLearnerBuffer.total_bytes(n, 5, 2), dtype=torch.uint8, device="cuda:0")
+    members = [PeerLearnerBuffer(sims[r], rank=r, world_size=2, buf=buf) for r in range(2)]
+    rng = np.random.default_rng(3)
+    for t in range(30):
+        acts = [torch.from_numpy(rng.uniform(-1, 1, (n, 4)).astype(np.float32)).cuda() + torch.cat(
+            [sims[r].env_offsets().cuda(), torch.zeros(n, 1, device="cuda")], 1) for r in range(2)]
+        members[1].step(acts[1])                      # the "remote" rank first, then the owner
+        members[0].step(acts[0])
+        members[0].step_no = members[1].step_no
+        rows = members[0].wait()
+        for r in range(2):
+            refs[r].step(acts[r])
+            assert torch.equal(rows[r][0], refs[r].obs) and torch.equal(rows[r][1], refs[r].reward)
+            assert torch.equal(rows[r][2], refs[r].done)
+    members[0].check()
+    # a flag that never arrives: the bounded wait gives up and reports which one
+    members[0].step_no += 1
+    members[0].wait(timeout_ms=20)
+    with pytest.raises(RuntimeError):
+        members[0].check()
+
+
 def test_fp32_gpu_vs_fp64_oracle_drift_within_tolerance():
     """north_star tolerance: <=1e-3 m / 1e-2 rad per step; drift over the 200-step horizon is reported."""
     n = 128
