@@ -40,8 +40,8 @@ SEED = 0
 # algorithmic cost per env-step (SURVEY.md 8d formula)
 BYTES_PER_ENV_STEP = 2 * 192 + 16 + 20 + 4 + 1   # float4-SoA state read+write (12 slots), action, obs, reward, done
 FLOPS_BULLET_DEFAULT = 2.2e5                       # I_ik=20, I_pgs=50, n=9, R=33
-NCU_EXECUTED_FLOPS_PER_ENV_STEP = 5.08e4          # ncu: (2*FFMA + FMUL + FADD thread-instructions) per launch / 4096 envs (profiles/r01_kstep_ws_ncu_full_v2.csv)
-NCU_TRAFFIC_BYTES = 948480                          # k_step_ws<panda>, 4096 envs: DRAM read 948 KB + write 0 B per launch (profiles/r01_kstep_ws_ncu_full_v2.csv)
+NCU_EXECUTED_FLOPS_PER_ENV_STEP = 5.11e4          # ncu: (2*FFMA + FMUL + FADD thread-instructions) per launch / 4096 envs (profiles/r01_kstep_ws_ncu_full_v3.csv)
+NCU_TRAFFIC_BYTES = 950272                          # k_step_ws<panda>, 4096 envs: DRAM read 950 KB + write 0 B per launch (profiles/r01_kstep_ws_ncu_full_v3.csv)
 
 
 def flops_per_env_step(n=9, na=7, i_ik=20, i_pgs=50, rows=17):
@@ -345,7 +345,7 @@ def main():
             "gpu_launches": args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (ach_tf / peak_tf) if peak_tf else None, "traffic": NCU_TRAFFIC_BYTES if (args.arm == "panda" and n == ENVS_PER_GPU) else None,
-                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_kstep_ws_ncu_full_v2.csv",
+                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_kstep_ws_ncu_full_v3.csv",
                          "peak_source": "in-run FFMA probe (pih_measure_fp32_peak); FP32 pipe is not in MEASURED_PEAKS.json",
                          "flops_per_env_step": f_run, "flops_per_env_step_bullet_default": FLOPS_BULLET_DEFAULT,
                          "executed_flops_per_env_step": NCU_EXECUTED_FLOPS_PER_ENV_STEP,
