@@ -167,6 +167,10 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(
   const int e = blockIdx.x * 32 + lane;
   const int ec = e < P.n ? e : P.n - 1;
   pdl_wait();
+  // the action row is requested first: with zero-copy host buffers it comes over PCIe, and the state load and the
+  // forward kinematics below hide that latency
+  float a[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  if (w == 0) load_action<A>(action, ec, a);
   EnvState S;
   load_state(P, ec, S);
   const bool active = (e < P.n) && !(S.flags & PIH_FLAG_DONE);
@@ -177,8 +181,6 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(
   fk<ARM, nb>(S.q, F);
   float qs[nb], kpc[nb], mfc[nb];
   if (w == 0) {
-    float a[6];
-    load_action<A>(action, ec, a);
     const bool fd = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc);
     mailbox_put<ARM, TASK>(mb, lane, qs, kpc, mfc, fd, S);
     PIH_TICK(1);
