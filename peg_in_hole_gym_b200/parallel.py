@@ -125,6 +125,8 @@ class PeerLearnerBuffer:
                 dist.barrier()
         self.timed_out = torch.zeros(1, dtype=torch.int32, device=sim.device)
         self.step_no = 0
+        self._rows = None
+        self._my_ptrs = self._ptrs(self.rank) + (self._flag_ptr(self.rank),)
 
     def close(self):
         if self._raw:
@@ -160,20 +162,24 @@ class PeerLearnerBuffer:
         ``sim``: another BatchedSim of the same size on this rank (several env batches may feed one learner buffer)."""
         from . import _native as N
         sim = self.sim if sim is None else sim
-        po, pr, pd = self._ptrs(self.rank)
+        po, pr, pd, pf = self._my_ptrs
         self.step_no += 1
-        st = sim._stream()
-        N.check(sim._L.pih_step_signal(sim._h, action.data_ptr(), po, pr, pd, self._flag_ptr(self.rank), self.step_no, st), sim._h,
-                "pih_step_signal")
+        rc = sim._L.pih_step_signal(sim._h, action.data_ptr(), po, pr, pd, pf, self.step_no, sim._stream())
+        if rc:
+            N.check(rc, sim._h, "pih_step_signal")
 
     def wait(self, timeout_ms=2000):
         """Rank 0: enqueue the wait for every rank's flag of the current step; returns [(obs, reward, done)] per rank
         (views of the learner buffer, valid for work enqueued after this call on the same stream)."""
         from . import _native as N
         sim = self.sim
-        N.check(sim._L.pih_wait_flags(sim._h, self.base + self.flag_off, self.world_size, self.step_no, int(timeout_ms),
-                                      self.timed_out.data_ptr(), sim._stream()), sim._h, "pih_wait_flags")
-        return [self._views(r) for r in range(self.world_size)]
+        rc = sim._L.pih_wait_flags(sim._h, self.base + self.flag_off, self.world_size, self.step_no, int(timeout_ms),
+                                   self.timed_out.data_ptr(), sim._stream())
+        if rc:
+            N.check(rc, sim._h, "pih_wait_flags")
+        if self._rows is None:     # the views never change: build them once (24 tensor slices cost more than a step)
+            self._rows = [self._views(r) for r in range(self.world_size)]
+        return self._rows
 
     def check(self):
         """Host-side: raises if a device-side wait gave up (synchronises the stream)."""
