@@ -305,13 +305,31 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # the same loop through the staged path (H2D copy, step, one D2H copy), for comparison with the zero-copy call
+    os.environ["PIH_NO_ZERO_COPY"] = "1"
+    sim_st = BatchedSim(n, task=args.task, arm=args.arm, sub_num=n, env_id_base=rank * nb_batches * n, offset=OFFSET, dt=dt_sim,
+                        seed=SEED, max_steps=MAX_STEPS, auto_reset=True, device=local)
+    del os.environ["PIH_NO_ZERO_COPY"]
+    sim_st.reset()
+    st_steps = min(e2e_steps, 400)
+    st_step = sim_st.host_stepper(h_acts, obs_h, rew_h, done_h)
+    for i in range(e2e_warm):
+        st_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(st_steps):
+        st_step(e2e_warm + i)
+        chk += float(rew_h[0]) + float(done_h[-1])
+    barrier()
+    staged_s = (time.perf_counter() - t0) * e2e_steps / st_steps     # scaled to e2e_steps for the common reduction below
+
     def reduce_max(x):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
-    dev_ms, roll_ms, e2e_s = reduce_max(dev_ms), reduce_max(roll_ms), reduce_max(e2e_s)
+    dev_ms, roll_ms, e2e_s, staged_s = reduce_max(dev_ms), reduce_max(roll_ms), reduce_max(e2e_s), reduce_max(staged_s)
     if rank == 0:
         total_envs = n * world
         value = total_envs * args.steps / (dev_ms * 1e-3)
@@ -341,7 +359,8 @@ def main():
                               if args.l2 == "rotate" else "flushed between timed steps (256 MiB memset); per-step CUDA events summed"),
                        "gather_to_rank0": args.gather or False, "parallelism": f"env-sharded x{world}, no data-path collective"},
             "e2e": {"value": total_envs * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * adim * 4,
-                    "d2h_bytes_per_step": n * (20 + 4 + 1), "steps": e2e_steps, "timing": "wall clock per step: pih_step_host on page-locked host buffers = one launch whose SMs read that step's actions from host memory and write obs|reward|done back to host memory over PCIe (zero-copy), stream sync, host reads the result; a fresh i.i.d. host action batch every step"},
+                    "d2h_bytes_per_step": n * (20 + 4 + 1), "steps": e2e_steps,
+                    "staged_copy_value": total_envs * e2e_steps / staged_s, "timing": "wall clock per step: pih_step_host on page-locked host buffers = one launch whose SMs read that step's actions from host memory and write obs|reward|done back to host memory over PCIe (zero-copy), stream sync, host reads the result; a fresh i.i.d. host action batch every step; staged_copy_value = the same loop with explicit cudaMemcpyAsync H2D + step + D2H"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (ach_tf / peak_tf) if peak_tf else None, "traffic": NCU_TRAFFIC_BYTES if (args.arm == "panda" and n == ENVS_PER_GPU) else None,
