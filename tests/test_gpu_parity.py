@@ -3,6 +3,8 @@ seeded inputs.  Bar (BASELINE.json north_star): discrete outputs (done flags, co
 episode/step counters) EXACT over a 200-step horizon; joint positions / EE / peg pose / reward within 1e-3 m,
 1e-2 rad per step - in practice the float oracle build and the kernels agree bit for bit, which is asserted where
 stated.  Drift of fp32 (GPU) against the fp64 oracle build is reported and bounded separately."""
+import os
+
 import numpy as np
 import pytest
 
@@ -339,6 +341,20 @@ def test_peer_write_gather_on_one_gpu_matches_plain_outputs():
     members[0].wait(timeout_ms=20)
     with pytest.raises(RuntimeError):
         members[0].check()
+
+
+def test_peer_write_gather_across_processes():
+    """Two rank processes share rank 0's learner buffer through CUDA IPC (pih_peer_alloc / pih_peer_open) and the step
+    kernels of both write into it; rank 0 checks every gathered row against locally recomputed steps.  Both ranks sit on
+    cuda:0 here (the driver's GPU tier has one GPU); on a multi-GPU node the same code maps the buffer as NVLink peer
+    memory (bench.py --gather peer)."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(here, "peer_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert "PEER_GATHER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
 
 
 def test_fp32_gpu_vs_fp64_oracle_drift_within_tolerance():
