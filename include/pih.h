@@ -31,7 +31,7 @@ extern "C" {
  * args, is_test) (README.md:38, base_env_mp.py:15, base_env.py:15) plus the NEW knobs of SURVEY.md Appendix D. */
 typedef struct pih_config {
   int32_t task;             /* 0 'peg-in-hole' (base_env.py:9-11), 1 'random-fly' (README.md:38) */
-  int32_t arm;              /* 0 panda (utils.py:30-38), 1 ur5 (utils.py:40-48) */
+  int32_t arm;              /* 0 panda (utils.py:30-38), 1 ur5 (utils.py:40-48; task 0 only) */
   int32_t fly_object;       /* args[0]: 0 'Banana', 1 'Amicelli' (README.md:38) */
   int32_t num_envs;         /* envs resident on this device = local mp_num * sub_num */
   int32_t sub_num;          /* envs per reference client; period of the offset layout (base_env.py:35-55) */

@@ -503,6 +503,9 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   if (cfg->num_envs <= 0 || cfg->sub_num <= 0) return PIH_ERR_INVALID;
   if (cfg->task != PIH_TASK_PEG_IN_HOLE && cfg->task != PIH_TASK_RANDOM_FLY && cfg->task != PIH_TASK_SCRIPTED) return PIH_ERR_INVALID;
   if (cfg->arm != PIH_ARM_PANDA && cfg->arm != PIH_ARM_UR5) return PIH_ERR_INVALID;
+  // the ur5 variant exists for the peg-in-hole task (utils.py:40-48,70-82); random-fly and the scripted episode are
+  // panda tasks (README.md:38, peg_in_hole.py:233), and their ur5 kernels are not instantiated
+  if (cfg->arm == PIH_ARM_UR5 && cfg->task != PIH_TASK_PEG_IN_HOLE) return PIH_ERR_INVALID;
   if (!(cfg->dt > 0.0f) || cfg->solver_iters < 0 || cfg->ik_iters < 0 || !(cfg->solver_residual >= 0.0f)) return PIH_ERR_INVALID;
   // reference assert: task_num == 1 or offset != [0,0,0] (envs/base_env.py:17)
   if (cfg->sub_num > 1 && cfg->offset[0] == 0.0f && cfg->offset[1] == 0.0f && cfg->offset[2] == 0.0f) return PIH_ERR_INVALID;
@@ -611,7 +614,7 @@ const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null hand
   do {                                                                            \
     int grid_ = ((h)->P.n + (h)->block - 1) / (h)->block;                         \
     if ((h)->P.arm == PIH_ARM_PANDA) LAUNCH_T(kern, PIH_ARM_PANDA, h, st, __VA_ARGS__); \
-    else LAUNCH_T(kern, PIH_ARM_UR5, h, st, __VA_ARGS__);                         \
+    else kern<PIH_ARM_UR5, PIH_TASK_PEG_IN_HOLE><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); /* ur5: peg-in-hole only (pih_create) */ \
   } while (0)
 #define LAUNCH_WS_T(kern, ARMV, h, st, ...)                                                                             \
   do {                                                                                                                 \
@@ -623,7 +626,7 @@ const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null hand
   do {                                                                            \
     int gridw_ = ((h)->P.n + 31) / 32;                                            \
     if ((h)->P.arm == PIH_ARM_PANDA) LAUNCH_WS_T(kern, PIH_ARM_PANDA, h, st, __VA_ARGS__); \
-    else LAUNCH_WS_T(kern, PIH_ARM_UR5, h, st, __VA_ARGS__);                      \
+    else launch_pdl(kern<PIH_ARM_UR5, PIH_TASK_PEG_IN_HOLE>, gridw_, 64, (cudaStream_t)(st), __VA_ARGS__); \
   } while (0)
 #endif
 #define LAUNCH_ARM(kern, h, st, ...)                                              \
