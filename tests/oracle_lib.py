@@ -101,8 +101,11 @@ class Oracle:
         self.done = np.zeros(self.n, np.uint8)
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().pih_oracle_destroy(self.h)
+        if getattr(self, "h", None) and _lib is not None:     # (module globals may already be gone at interpreter exit)
+            try:
+                _lib.pih_oracle_destroy(self.h)
+            except Exception:
+                pass
             self.h = None
 
     def reset(self, mask=None):
