@@ -135,6 +135,12 @@ class PeerLearnerBuffer:
             self.sim._L.pih_peer_release(self._raw, int(self._owner))
             self._raw = None
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     @staticmethod
     def total_bytes(n, obs_dim, world_size):
         raw = n * obs_dim * 4 + n * 4 + n

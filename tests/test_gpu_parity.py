@@ -350,9 +350,13 @@ def test_peer_write_gather_across_processes():
     memory (bench.py --gather peer)."""
     import subprocess
     import sys
+    import socket
     here = os.path.dirname(os.path.abspath(__file__))
+    with socket.socket() as sk:                      # a free rendezvous port
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29533", os.path.join(here, "peer_worker.py")]
+           "--master-port", str(port), os.path.join(here, "peer_worker.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert "PEER_GATHER_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
 
