@@ -81,6 +81,60 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOC
   if (done) done[e] = d;
 }
 
+// ---- large batches, split step: apply_action (FK -> vel_constraint -> IK) needs far fewer registers than the dynamics,
+// so it runs as its own kernel at 2-3x the occupancy and hands the joint targets over through a small SoA scratch
+// buffer ([nb][n] floats, 36 B per env); the dynamics kernel is the classic step without the IK code.  Same functions,
+// same arithmetic as the fused k_step.  The scripted task keeps the fused kernel (its state machine lives in apply_action).
+#ifndef PIH_ACTION_MIN_BLOCKS
+#define PIH_ACTION_MIN_BLOCKS 3
+#endif
+template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_ACTION_MIN_BLOCKS) k_apply_action(SimParams P, const float* __restrict__ action,
+                                                                                                   float* __restrict__ qt) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.n) return;
+  constexpr int A = ArmDims<ARM>::ADIM, nb = ArmDims<ARM>::NB;
+  float a[6];
+  load_action<A>(action, e, a);
+  EnvState S;
+  load_state(P, e, S);
+  if (S.flags & PIH_FLAG_DONE) return;     // frozen env: the dynamics kernel will not read its targets
+  FK<ARM> F;
+  fk<ARM, nb>(S.q, F);
+  float qs[nb], kpc[nb], mfc[nb];
+  apply_action<ARM, TASK>(P, S, F, a, env_offset(P, e), qs, kpc, mfc);
+#pragma unroll
+  for (int j = 0; j < nb; ++j) qt[(size_t)j * P.n + e] = qs[j];
+}
+
+template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOCKS) k_step_dyn(SimParams P, const float* __restrict__ qt, float* __restrict__ obs,
+                                                                    float* __restrict__ reward, unsigned char* __restrict__ done) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.n) return;
+  constexpr int nb = ArmDims<ARM>::NB;
+  const ArmTables& T = c_arm[ARM];
+  EnvState S;
+  load_state(P, e, S);
+  const v3 off = env_offset(P, e);
+  float o[5], r;
+  unsigned char d;
+  if (S.flags & PIH_FLAG_DONE) frozen_outputs<ARM>(S, off, o, r, d);
+  else {
+    FK<ARM> F;
+    fk<ARM, nb>(S.q, F);
+    float qs[nb], kpc[nb], mfc[nb];
+#pragma unroll
+    for (int j = 0; j < nb; ++j) { qs[j] = __ldg(&qt[(size_t)j * P.n + e]); kpc[j] = T.kp[j]; mfc[j] = T.maxf[j]; }
+    step_back<ARM, TASK>(P, S, F, qs, kpc, mfc, false, true, off, (unsigned)(P.env_id_base + e), o, r, d);
+    store_state(P, e, S);
+  }
+  if (obs) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) obs[5 * (size_t)e + k] = o[k];
+  }
+  if (reward) reward[e] = r;
+  if (done) done[e] = d;
+}
+
 template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOCKS) k_rollout(SimParams P, int steps, float* __restrict__ obs, float* __restrict__ reward,
                                                                    unsigned char* __restrict__ done, unsigned long long* __restrict__ counters) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -396,6 +450,8 @@ struct pih_handle {
   float *d_action, *d_obs, *d_reward;
   unsigned char* d_done;
   float* d_scene;  // render pre-pass output [n][PIH_SCENE_WORDS], allocated on first pih_render
+  float* d_qt;     // joint targets [nb][n] between k_apply_action and k_step_dyn (large batches), allocated on first use
+  int split;       // large batches: step = k_apply_action + k_step_dyn (0: fused k_step; env PIH_SPLIT overrides)
   // host pointer -> mapped device alias cache of pih_step_host
   const void* alias_host[PIH_ALIAS_SLOTS];
   void* alias_dev[PIH_ALIAS_SLOTS];
@@ -558,6 +614,11 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   h->ws = (P.n <= 148 * 32 * 4) ? 1 : 0;
   const char* wse = getenv("PIH_WS");
   if (wse) h->ws = atoi(wse) ? 1 : 0;
+  // measured (tools/split_probe.py): fused 216 / 434 / 781 us against split 196 / 378 / 692 us per step at 65536 /
+  // 131072 / 262144 envs; below ~2 waves of the fused kernel the extra launch does not pay (104 vs 106 us at 32768)
+  h->split = (P.n >= 49152) ? 1 : 0;
+  const char* spe = getenv("PIH_SPLIT");
+  if (spe) h->split = atoi(spe) ? 1 : 0;
   const char* nz = getenv("PIH_NO_ZERO_COPY");   // diagnostics: force the staged-copy host path
   if (nz) h->no_zero_copy = atoi(nz) ? 1 : 0;
   const char* bs = getenv("PIH_BLOCK");
@@ -575,6 +636,7 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
 void pih_destroy(pih_handle* h) {
   if (!h) return;
   if (h->d_cta_counter) cudaFree(h->d_cta_counter);
+  if (h->d_qt) cudaFree(h->d_qt);
   if (h->h_action) cudaFreeHost(h->h_action);
   if (h->h_obs) cudaFreeHost(h->h_obs);     // one pinned block: obs | reward | done
   if (h->d_action) cudaFree(h->d_action);
@@ -629,6 +691,18 @@ const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null hand
     else launch_pdl(kern<PIH_ARM_UR5, PIH_TASK_PEG_IN_HOLE>, gridw_, 64, (cudaStream_t)(st), __VA_ARGS__); \
   } while (0)
 #endif
+// peg-in-hole / random-fly only (kernels that are never instantiated for the scripted task)
+#ifdef PIH_FAST_BUILD
+#define LAUNCH_PF(kern, h, st, ...) LAUNCH(kern, h, st, __VA_ARGS__)
+#else
+#define LAUNCH_PF(kern, h, st, ...)                                               \
+  do {                                                                            \
+    int grid_ = ((h)->P.n + (h)->block - 1) / (h)->block;                         \
+    if ((h)->P.arm == PIH_ARM_UR5) kern<PIH_ARM_UR5, PIH_TASK_PEG_IN_HOLE><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
+    else if ((h)->P.task == PIH_TASK_RANDOM_FLY) kern<PIH_ARM_PANDA, PIH_TASK_RANDOM_FLY><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
+    else kern<PIH_ARM_PANDA, PIH_TASK_PEG_IN_HOLE><<<grid_, (h)->block, 0, (cudaStream_t)(st)>>>(__VA_ARGS__); \
+  } while (0)
+#endif
 #define LAUNCH_ARM(kern, h, st, ...)                                              \
   do {                                                                            \
     int grid_ = ((h)->P.n + (h)->block - 1) / (h)->block;                         \
@@ -668,7 +742,14 @@ static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, flo
   const StepSignal sig = {flag_dev, flag_value, h->d_cta_counter};
   if (h->ws) { LAUNCH_WS(k_step_ws, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev, sig); }
   else {
-    LAUNCH(k_step, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev);
+    if (h->split && h->P.task != PIH_TASK_SCRIPTED) {
+      if (!h->d_qt && cudaMalloc(&h->d_qt, (size_t)h->P.n * PIH_NB_MAX * sizeof(float)) != cudaSuccess)
+        return fail(h, PIH_ERR_CUDA, "target scratch allocation", cudaGetLastError());
+      LAUNCH_PF(k_apply_action, h, stream, h->P, action_dev, h->d_qt);
+      LAUNCH_PF(k_step_dyn, h, stream, h->P, h->d_qt, obs_dev, reward_dev, done_dev);
+    } else {
+      LAUNCH(k_step, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev);
+    }
     if (flag_dev) k_signal_flag<<<1, 1, 0, (cudaStream_t)stream>>>(flag_dev, flag_value);   // large batches: the extra launch is noise
   }
   cudaError_t ce = cudaGetLastError();
