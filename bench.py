@@ -361,7 +361,8 @@ def main():
             "e2e": {"value": total_envs * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * adim * 4,
                     "d2h_bytes_per_step": n * (20 + 4 + 1), "steps": e2e_steps,
                     "staged_copy_value": total_envs * e2e_steps / staged_s, "timing": "wall clock per step: pih_step_host on page-locked host buffers = one launch whose SMs read that step's actions from host memory and write obs|reward|done back to host memory over PCIe (zero-copy), stream sync, host reads the result; a fresh i.i.d. host action batch every step; staged_copy_value = the same loop with explicit cudaMemcpyAsync H2D + step + D2H"},
-            "gpu_launches": args.steps,
+            # one step kernel per env.step; from 49152 envs per GPU on the step is two launches (k_apply_action + k_step_dyn)
+            "gpu_launches": args.steps * (2 if n >= 49152 else 1),
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (ach_tf / peak_tf) if peak_tf else None, "traffic": NCU_TRAFFIC_BYTES if (args.arm == "panda" and n == ENVS_PER_GPU) else None,
                          "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_kstep_ws_ncu_full_v3.csv",
@@ -372,7 +373,7 @@ def main():
                          "frac_executed": (NCU_EXECUTED_FLOPS_PER_ENV_STEP * n / kern_s / 1e12 / peak_tf) if peak_tf else None,
                          "note": "achieved/frac use SURVEY 8(d)'s algorithmic FLOP model; *_executed use the FP32 thread-instructions ncu counted "
                                  "(the implementation skips structural zeros and reuses the ABA factorisation, so it executes well under half)",
-                         "kernel": ("pih::k_step_ws" if n <= 148 * 64 else "pih::k_step") + f"<{args.arm}, {args.task}>", "kernel_us": kern_s * 1e6,
+                         "kernel": ("pih::k_step_ws" if n <= 148 * 128 else ("pih::k_step" if n < 49152 else "pih::k_apply_action + pih::k_step_dyn")) + f"<{args.arm}, {args.task}>", "kernel_us": kern_s * 1e6,
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"}},
             "cpu_baseline": cpu,

@@ -10,7 +10,7 @@ from peg_in_hole_gym_b200.sim import BatchedSim  # noqa: E402
 
 arm = sys.argv[1] if len(sys.argv) > 1 else "panda"
 adim = 4 if arm == "panda" else 6
-for n in (24576, 32768, 65536, 131072, 262144):
+for n in [int(v) for v in os.environ.get('SIZES', '24576,32768,65536,131072,262144').split(',')]:
     res = []
     for split in ("0", "1"):
         os.environ["PIH_SPLIT"] = split
