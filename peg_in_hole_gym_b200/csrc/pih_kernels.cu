@@ -93,21 +93,33 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_ACTION_M
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.n) return;
   constexpr int A = ArmDims<ARM>::ADIM, nb = ArmDims<ARM>::NB;
-  float a[6];
-  load_action<A>(action, e, a);
+  float a[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  const v3 off = env_offset(P, e);
+  if (action) load_action<A>(action, e, a);
+  else {   // synthetic rollouts: action_space.sample() ~ U[-1,1]^A from Philox (seed; env, global step), as in k_rollout
+    const unsigned gid = (unsigned)(P.env_id_base + e);
+    float u[8], u0[4];
+    rng4(P, gid, P.global_step, PIH_STREAM_ACTION, u0);
+    u[0] = u0[0]; u[1] = u0[1]; u[2] = u0[2]; u[3] = u0[3];
+    if (A > 4) { rng4(P, gid, P.global_step, PIH_STREAM_ACTION + 1, u0); u[4] = u0[0]; u[5] = u0[1]; u[6] = u0[2]; u[7] = u0[3]; }
+#pragma unroll
+    for (int k = 0; k < A; ++k) a[k] = fmaf(u[k], 2.0f, -1.0f);
+    if (!P.action_frame_env) { a[0] += off.x; a[1] += off.y; a[2] += off.z; }
+  }
   EnvState S;
   load_state(P, e, S);
   if (S.flags & PIH_FLAG_DONE) return;     // frozen env: the dynamics kernel will not read its targets
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
   float qs[nb], kpc[nb], mfc[nb];
-  apply_action<ARM, TASK>(P, S, F, a, env_offset(P, e), qs, kpc, mfc);
+  apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc);
 #pragma unroll
   for (int j = 0; j < nb; ++j) qt[(size_t)j * P.n + e] = qs[j];
 }
 
 template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOCKS) k_step_dyn(SimParams P, const float* __restrict__ qt, float* __restrict__ obs,
-                                                                    float* __restrict__ reward, unsigned char* __restrict__ done) {
+                                                                    float* __restrict__ reward, unsigned char* __restrict__ done,
+                                                                    unsigned long long* __restrict__ counters) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.n) return;
   constexpr int nb = ArmDims<ARM>::NB;
@@ -117,6 +129,7 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOC
   const v3 off = env_offset(P, e);
   float o[5], r;
   unsigned char d;
+  unsigned nsteps = 0, ndone = 0;
   if (S.flags & PIH_FLAG_DONE) frozen_outputs<ARM>(S, off, o, r, d);
   else {
     FK<ARM> F;
@@ -126,6 +139,12 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOC
     for (int j = 0; j < nb; ++j) { qs[j] = __ldg(&qt[(size_t)j * P.n + e]); kpc[j] = T.kp[j]; mfc[j] = T.maxf[j]; }
     step_back<ARM, TASK>(P, S, F, qs, kpc, mfc, false, true, off, (unsigned)(P.env_id_base + e), o, r, d);
     store_state(P, e, S);
+    nsteps = 1; ndone = d;
+  }
+  if (counters) {   // rollout accounting: one atomic pair per warp
+    const unsigned m = __activemask();
+    unsigned ws = __reduce_add_sync(m, nsteps), wd = __reduce_add_sync(m, ndone);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1) && ws) { atomicAdd(&counters[0], (unsigned long long)ws); atomicAdd(&counters[1], (unsigned long long)wd); }
   }
   if (obs) {
 #pragma unroll
@@ -746,7 +765,7 @@ static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, flo
       if (!h->d_qt && cudaMalloc(&h->d_qt, (size_t)h->P.n * PIH_NB_MAX * sizeof(float)) != cudaSuccess)
         return fail(h, PIH_ERR_CUDA, "target scratch allocation", cudaGetLastError());
       LAUNCH_PF(k_apply_action, h, stream, h->P, action_dev, h->d_qt);
-      LAUNCH_PF(k_step_dyn, h, stream, h->P, h->d_qt, obs_dev, reward_dev, done_dev);
+      LAUNCH_PF(k_step_dyn, h, stream, h->P, h->d_qt, obs_dev, reward_dev, done_dev, (unsigned long long*)nullptr);
     } else {
       LAUNCH(k_step, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev);
     }
@@ -848,6 +867,19 @@ int pih_rollout(pih_handle* h, int32_t steps, float* obs_dev, float* reward_dev,
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "rollout() before reset()", cudaSuccess);
   if (use_device(h)) return PIH_ERR_CUDA;
   if (h->ws) { LAUNCH_WS(k_rollout_ws, h, stream, h->P, (int)steps, obs_dev, reward_dev, done_dev, counters_dev); }
+  else if (h->split && h->P.task != PIH_TASK_SCRIPTED) {
+    // large batches: the two-kernel step (see k_apply_action), `steps` times; at these sizes a launch is noise
+    if (!h->d_qt && cudaMalloc(&h->d_qt, (size_t)h->P.n * PIH_NB_MAX * sizeof(float)) != cudaSuccess)
+      return fail(h, PIH_ERR_CUDA, "target scratch allocation", cudaGetLastError());
+    for (int t = 0; t < steps; ++t) {
+      LAUNCH_PF(k_apply_action, h, stream, h->P, (const float*)nullptr, h->d_qt);
+      LAUNCH_PF(k_step_dyn, h, stream, h->P, h->d_qt, obs_dev, reward_dev, done_dev, counters_dev);
+      h->P.global_step += 1;
+    }
+    cudaError_t ce2 = cudaGetLastError();
+    if (ce2 != cudaSuccess) return fail(h, PIH_ERR_CUDA, "split rollout launch", ce2);
+    return PIH_OK;
+  }
   else { LAUNCH(k_rollout, h, stream, h->P, (int)steps, obs_dev, reward_dev, done_dev, counters_dev); }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_rollout launch", ce);
