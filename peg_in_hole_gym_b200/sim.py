@@ -13,7 +13,7 @@ from . import _native as N
 
 class BatchedSim:
     """num_envs sub-environments resident on one GPU.  State lives in a torch-owned float4-SoA tensor
-    ``state[10, N, 4]`` (layout: csrc/pih_constants.h); outputs in ``obs[N,5]``, ``reward[N]``, ``done[N]``."""
+    ``state[12, N, 4]`` (layout: csrc/pih_constants.h); outputs in ``obs[N,5]``, ``reward[N]``, ``done[N]``."""
 
     def __init__(self, num_envs, task="peg-in-hole", arm="panda", fly_object="banana", sub_num=None, env_id_base=0,
                  offset=(0.0, 0.0, 0.0), dt=1.0 / 240.0, solver_residual=1e-7, solver_iters=50, ik_iters=20, max_steps=0, auto_reset=False,
