@@ -283,3 +283,31 @@ def test_grasp_label_images_follow_random_grasp():
     ins = lab[:, 0] == 50.0
     assert ins.any(axis=(1, 2)).all()
     assert (ins[:, 1:, 1:] == ins[:, 1:, 1:][:, ::-1, ::-1]).mean() > 0.98   # point symmetry about (W/2, H/2)
+
+
+@pytest.mark.parametrize("dbl", [False, True])
+def test_frictionless_impact_keeps_tangential_velocity_and_pushes_out_with_erp(dbl):
+    """banana.urdf:5-6 has lateral_friction 0: hitting the table must leave the tangential velocity untouched, and the
+    normal velocity after the solve is the push-out bias ERP * penetration / dt of a penetrating contact (Bullet's
+    contact ERP 0.2 [3P]); a flat box on four symmetric corner contacts picks up no spin.  Closed forms, exact to rounding."""
+    dt = 1.0 / 120.0
+    o = ol.Oracle(ol.make_config(1, task=1, fly_object=0, dt=dt, seed=1), use_double=dbl)
+    o.reset()
+    hz, table = 0.0187, -0.05
+    _set(o, 1, pos=(ol.S_PPOS, [[0.3, -0.3, table + hz + 0.004]]), vel=(ol.S_PVEL, [[1.5, -0.7, -1.0]]),
+         ang=(ol.S_PANG, [[0.0, 0.0, 0.0]]), quat=(ol.S_PQUAT, [[0.0, 0.0, 0.0, 1.0]]))
+    a = np.zeros((1, 4), np.float32); a[:, :3] = o.obs[:, 2:5]; a[:, 3] = 0.04
+    o.step(a)                                   # 4 mm above the table: outside the 2 mm margin, pure free fall
+    w = o.get_state()
+    v1 = ol.state_field(w, ol.S_PVEL, 3)[0]
+    z1 = ol.state_field(w, ol.S_PPOS, 3)[0, 2]
+    assert np.allclose(v1, [1.5, -0.7, -1.0 - 9.8 * dt], atol=1e-6) and not (ol.state_int(w, ol.S_FLAGS)[0] >> 8)
+    pen = table - (z1 - hz)
+    assert pen > 0.004                          # it tunnelled: the next step sees a penetrating contact
+    _, r, d = o.step(a)
+    w = o.get_state()
+    v2, om = ol.state_field(w, ol.S_PVEL, 3)[0], ol.state_field(w, ol.S_PANG, 3)[0]
+    assert (ol.state_int(w, ol.S_FLAGS)[0] >> 8) & 1 and d[0] == 1          # table impact ends the random-fly episode
+    assert abs(v2[0] - 1.5) < 1e-6 and abs(v2[1] + 0.7) < 1e-6              # mu = 0: no tangential impulse at all
+    assert abs(v2[2] - 0.2 * pen / dt) < 2e-4                                # ERP push-out velocity
+    assert np.abs(om).max() < 1e-3
