@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define PIH_ABI_VERSION 1
+#define PIH_ABI_VERSION 2
 
 /* error codes */
 #define PIH_OK 0
@@ -47,7 +47,16 @@ typedef struct pih_config {
   int32_t action_frame_env; /* NEW 0 = reference (actions are absolute world coordinates), 1 = relative to env origin */
   int32_t device;           /* CUDA device ordinal */
   uint64_t seed;            /* Philox key (reference: unseeded global MT19937, peg_in_hole.py:239) */
+  int32_t kernel_family;    /* NEW which step kernels run: 0 = chosen from num_envs (default), 1 = warp-specialised small-batch kernels,
+                               2 = fused thread-per-env kernel, 3 = split apply_action + dynamics kernels.  All families compute the
+                               same bits (tests/test_gpu_parity.py); the field exists so that every family can be tested at any size */
+  int32_t host_path;        /* NEW pih_step_host: 0 = zero-copy when the caller's buffers are page-locked, else staged; 1 = always staged */
 } pih_config;
+
+#define PIH_KERNELS_AUTO 0
+#define PIH_KERNELS_WARP_SPECIALISED 1
+#define PIH_KERNELS_FUSED 2
+#define PIH_KERNELS_SPLIT 3
 
 typedef struct pih_handle pih_handle;
 
@@ -85,6 +94,19 @@ int pih_step(pih_handle* h, const float* action_dev, float* obs_dev, float* rewa
  * the handle's pinned block: H2D, step, ONE D2H of [obs n*5 f32 | reward n f32 | done n u8].  Done envs re-emit their
  * last outputs (they are a function of the frozen state), so the output buffers may be fresh every call. */
 int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host, void* stream);
+
+/* Lifetime contract for the zero-copy path of pih_step_host.  A page-locked, device-mapped host range that the caller
+ * BINDS stays resolved inside the handle (no per-call driver query) until it is unbound; the caller guarantees that the
+ * memory stays allocated and registered for that long.  Buffers that are not bound are looked up in the driver on every
+ * call, so a stale answer can never be used.  host_ptr == NULL in pih_host_unbind drops every binding. */
+int pih_host_bind(pih_handle* h, const void* host_ptr, uint64_t bytes);
+int pih_host_unbind(pih_handle* h, const void* host_ptr);
+
+/* Execution statistics (NEW; measurement only).  stats_dev: nullable device uint64[8]; while set, every
+ * step / rollout kernel adds to it: [0] env-steps, [1] IK iterations executed, [2] constraint rows solved summed over
+ * solver iterations, [3] solver iterations, [4] contact points, [5] joint-limit rows, [6] envs force-reset by the
+ * non-finite guard, [7] max solver iterations of any env-step.  The caller zeroes and reads the buffer. */
+int pih_set_stats(pih_handle* h, unsigned long long* stats_dev);
 
 /* Benchmark / synthetic rollouts: `steps` consecutive env.steps in ONE launch with actions
  * action_space.sample() ~ U[-1,1]^A (README.md:48) drawn in-kernel from Philox (seed; env, global step).

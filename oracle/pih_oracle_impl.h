@@ -920,13 +920,19 @@ static void FN(reset_env)(const model* M, const simcfg* C, envstate* S, uint32_t
     S->pvel[0] = S->pvel[1] = S->pvel[2] = RC(0);
   } else {
     /* random-fly (NEW, source missing from the reference snapshot): the object is thrown from
-     * 1.2 m out at a random azimuth so that it passes through random_pos_in_panda_space() (envs/utils.py:97-107,
-     * here sampled without rejection: x in (-.7,.7), y = +-sqrt(U(0,.49-x^2)), z on the sphere) after 0.5 s */
-    float x = fmaf(u[0], 1.4f, -0.7f);
-    float y2 = u[1] * (0.49f - x * x);
-    y2 = y2 > 0.0f ? y2 : 0.0f;
-    float y = sqrtf(y2) * ((u[2] < 0.5f) ? -1.0f : 1.0f);
-    float zz = 0.49f - x * x - y2;
+     * 1.2 m out at a random azimuth so that it passes through random_pos_in_panda_space() (envs/utils.py:97-107:
+     * x ~ U(-.7,.7), y = (sqrt(U(0,.49-x^2)) - U(0,.4)) * choice(+-1), rejected while .49-x^2-y^2 < 0, z on the
+     * sphere + 0.2; the rejection loop is bounded by PIH_FLY_MAX_ATTEMPTS, NEW) after 0.5 s */
+    float x = 0.0f, y = 0.0f, zz = 0.49f;
+    for (int k = 0; k < PIH_FLY_MAX_ATTEMPTS; ++k) {   /* the `while` loop of utils.py:101-104, attempt k = Philox stream FLY + k */
+      float v[4];
+      pih_rng4(C->seed, gid, (uint32_t)S->episode, PIH_STREAM_FLY + k, v);
+      const float xk = fmaf(v[0], 1.4f, -0.7f);                         /* random.uniform(-length, length) */
+      const float a2 = fmaf(-xk, xk, 0.49f);
+      const float yk = (sqrtf(v[1] * (a2 > 0.0f ? a2 : 0.0f)) - v[2] * 0.4f) * ((v[3] < 0.5f) ? -1.0f : 1.0f);
+      const float rem = fmaf(-yk, yk, a2);
+      if (!(rem < 0.0f)) { x = xk; y = yk; zz = rem; break; }
+    }
     float z = sqrtf(zz > 0.0f ? zz : 0.0f) + 0.2f;
     float ca, sa;
     pih_sincosf_det(u[3] * 6.2831855f, &sa, &ca);
@@ -1430,6 +1436,23 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
     for (int i = 0; i < 4; ++i) S->pquat[i] = nq[i] * in;
   }
   S->step += 1;
+  /* ---- fault guard (NEW): non-finite state -> re-initialise the env (new episode), report done
+   * with reward 0, flag PIH_FLAG_FAULT; without auto_reset the env then stays frozen at the fresh state until reset() */
+  {
+    int finite = 1;
+    for (int j = 0; j < nb; ++j) finite = finite && isfinite(S->q[j]) && isfinite(S->qd[j]);
+    for (int k = 0; k < 3; ++k) finite = finite && isfinite(S->ppos[k]) && isfinite(S->pvel[k]) && isfinite(S->pang[k]);
+    for (int k = 0; k < 4; ++k) finite = finite && isfinite(S->pquat[k]);
+    if (!finite) {
+      S->episode += 1;
+      FN(reset_env)(M, C, S, gid);
+      S->flags = PIH_FLAG_FAULT | (C->auto_reset ? 0 : PIH_FLAG_DONE);
+      *reward = RC(0);
+      *done = 1;
+      FN(observe)(M, C, S, off, obs);
+      return CS.n;
+    }
+  }
   /* ---- get_info: observation, reward, done (envs/peg_in_hole.py:13,114-117; time limit NEW) ---- */
   real rew = RC(0);
   int success = 0;
@@ -1460,7 +1483,7 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
     int keep = S->flags & ~PIH_FLAG_DONE;
     S->episode += 1;
     FN(reset_env)(M, C, S, gid);
-    S->flags = keep & ~0xff; /* contact mask of the terminal step stays visible; done/success cleared */
+    S->flags = (keep & ~0xff) | (success ? PIH_FLAG_PREV_SUCCESS : 0); /* contact mask of the terminal step stays visible; done/success cleared */
     FN(observe)(M, C, S, off, obs);
   } else {
     obs[0] = (nb > M->narm) ? S->q[M->narm] : RC(0);

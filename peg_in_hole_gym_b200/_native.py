@@ -23,7 +23,7 @@ class PihConfig(C.Structure):
                 ("sub_num", C.c_int32), ("env_id_base", C.c_int32), ("offset", C.c_float * 3), ("dt", C.c_float), ("solver_residual", C.c_float),
                 ("solver_iters", C.c_int32), ("ik_iters", C.c_int32), ("max_steps", C.c_int32),
                 ("auto_reset", C.c_int32), ("action_frame_env", C.c_int32), ("device", C.c_int32),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("kernel_family", C.c_int32), ("host_path", C.c_int32)]
 
 
 class NativeLibraryMissing(ImportError):
@@ -58,6 +58,9 @@ def lib():
     L.pih_step.argtypes = [vp, vp, vp, vp, vp, vp]
     L.pih_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.pih_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.pih_host_bind.argtypes = [vp, vp, C.c_uint64]
+    L.pih_host_unbind.argtypes = [vp, vp]
+    L.pih_set_stats.argtypes = [vp, vp]
     L.pih_ik_targets.argtypes = [vp, vp, vp, vp]
     L.pih_ee_pose.argtypes = [vp, vp, vp, vp]
     L.pih_render.argtypes = [vp, i32, i32, vp, vp]
@@ -72,9 +75,10 @@ def lib():
     L.pih_measure_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     for name in ("pih_create", "pih_env_offset", "pih_reset", "pih_step", "pih_step_host", "pih_rollout",
                  "pih_ik_targets", "pih_ee_pose", "pih_measure_fp32_peak", "pih_action_dim", "pih_render", "pih_grasp_labels",
-                 "pih_step_signal", "pih_peer_alloc", "pih_peer_open", "pih_peer_release", "pih_enable_peer", "pih_signal_flag", "pih_wait_flags"):
+                 "pih_step_signal", "pih_peer_alloc", "pih_peer_open", "pih_peer_release", "pih_enable_peer", "pih_signal_flag", "pih_wait_flags",
+                 "pih_host_bind", "pih_host_unbind", "pih_set_stats"):
         getattr(L, name).restype = C.c_int
-    if L.pih_abi_version() != 1:
+    if L.pih_abi_version() != 2:
         raise ImportError("libpih_b200.so ABI version mismatch")
     _lib = L
     return L
@@ -84,13 +88,16 @@ EXPORTS = ["pih_abi_version", "pih_state_words", "pih_action_dim", "pih_obs_dim"
            "pih_last_error", "pih_env_offset", "pih_reset", "pih_step", "pih_step_host", "pih_rollout",
            "pih_ik_targets", "pih_ee_pose", "pih_render", "pih_grasp_labels", "pih_step_signal", "pih_peer_alloc", "pih_peer_open", "pih_peer_release",
            "pih_enable_peer", "pih_signal_flag",
-           "pih_wait_flags", "pih_measure_fp32_peak"]
+           "pih_wait_flags", "pih_measure_fp32_peak", "pih_host_bind", "pih_host_unbind", "pih_set_stats"]
+KERNEL_FAMILIES = {"auto": 0, "ws": 1, "fused": 2, "split": 3}
 
 
 def make_config(num_envs, task="peg-in-hole", arm="panda", fly_object="banana", sub_num=None, env_id_base=0,
                 offset=(0.0, 0.0, 0.0), dt=1.0 / 240.0, solver_residual=1e-7, solver_iters=50, ik_iters=20, max_steps=0, auto_reset=False,
-                action_frame_env=False, device=0, seed=0):
+                action_frame_env=False, device=0, seed=0, kernel_family="auto", host_path=0):
     c = PihConfig()
+    c.kernel_family = KERNEL_FAMILIES[kernel_family] if isinstance(kernel_family, str) else int(kernel_family)
+    c.host_path = int(host_path)
     c.task = TASK_IDS[task] if isinstance(task, str) else int(task)
     c.arm = ARM_IDS[arm] if isinstance(arm, str) else int(arm)
     c.fly_object = FLY_OBJECTS[fly_object.lower()] if isinstance(fly_object, str) else int(fly_object)

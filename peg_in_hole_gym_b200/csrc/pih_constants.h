@@ -28,6 +28,10 @@
 
 #define PIH_FLAG_DONE 1
 #define PIH_FLAG_SUCCESS 2
+#define PIH_FLAG_FAULT 4        /* NEW: a non-finite value appeared in the env's state during the step; the env
+                                   was re-initialised in the same launch (new episode), reported done with reward 0 */
+#define PIH_FLAG_PREV_SUCCESS 8 /* NEW, auto_reset only: the episode that ended in the step that set this word ended in success
+                                   (the success bit itself is cleared together with done when the env restarts) */
 #define PIH_PAIR_SHIFT 8
 #define PIH_PAIR_PEG_TABLE 1    /* contact-pair presence bits (<< PIH_PAIR_SHIFT) */
 #define PIH_PAIR_PEG_HOLE 2
@@ -117,6 +121,19 @@
 
 /* RNG stream ids (Philox4x32-10 counter word 2) */
 #define PIH_STREAM_RESET 0
-#define PIH_STREAM_ACTION 1
+#define PIH_STREAM_ACTION 1     /* (+1 for the second half of a Box(6) action) */
+#define PIH_STREAM_FLY 8        /* 8 + k: attempt k of the rejection loop of random_pos_in_panda_space (envs/utils.py:97-107) */
+#define PIH_FLY_MAX_ATTEMPTS 8  /* NEW bound on that loop (a rejection has probability ~3 %: 8 in a row never happens in practice) */
+#define PIH_STREAM_PIPE 16      /* 16..: pipe bends and grasp link at reset (peg_in_hole.py:244-245,266) */
+
+/* pih_set_stats counters (uint64[8]), accumulated by the step / rollout kernels when a buffer is set */
+#define PIH_STAT_ENV_STEPS 0
+#define PIH_STAT_IK_ITERS 1     /* damped-least-squares updates executed */
+#define PIH_STAT_PGS_ROW_ITERS 2 /* constraint rows solved, summed over iterations (a converged island's rows do not count) */
+#define PIH_STAT_PGS_ITERS 3    /* solver iterations until the env's last island converged */
+#define PIH_STAT_CONTACTS 4     /* contact points (3 rows each) */
+#define PIH_STAT_LIMIT_ROWS 5
+#define PIH_STAT_FAULTS 6       /* envs force-reset by the non-finite guard */
+#define PIH_STAT_PGS_ITERS_MAX 7
 
 #endif

@@ -112,7 +112,9 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_ACTION_M
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
   float qs[nb], kpc[nb], mfc[nb];
-  apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc);
+  int ik_n;
+  apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc, ik_n);
+  stat_add(P, PIH_STAT_IK_ITERS, (unsigned)ik_n);
 #pragma unroll
   for (int j = 0; j < nb; ++j) qt[(size_t)j * P.n + e] = qs[j];
 }
@@ -254,8 +256,10 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(
   fk<ARM, nb>(S.q, F);
   float qs[nb], kpc[nb], mfc[nb];
   if (w == 0) {
-    const bool fd = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc);
+    int ik_n;
+    const bool fd = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc, ik_n);
     mailbox_put<ARM, TASK>(mb, lane, qs, kpc, mfc, fd, S);
+    stat_add(P, PIH_STAT_IK_ITERS, active ? (unsigned)ik_n : 0u);
     PIH_TICK(1);
     __syncthreads();
     return;
@@ -332,8 +336,10 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_rollout_
 #pragma unroll
       for (int k = 0; k < A; ++k) a[k] = fmaf(u[k], 2.0f, -1.0f);
       if (!P.action_frame_env) { a[0] += off.x; a[1] += off.y; a[2] += off.z; }
-      const bool fd = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc);
+      int ik_n;
+      const bool fd = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc, ik_n);
       mailbox_put<ARM, TASK>(mb, lane, qs, kpc, mfc, fd, S);
+      stat_add(P, PIH_STAT_IK_ITERS, active ? (unsigned)ik_n : 0u);
       __syncthreads();   // A: targets ready
       __syncthreads();   // B: new state published by the dynamics warp
       load_state_smem(st, lane, S);
@@ -380,7 +386,8 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128) k_ik(SimPara
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
   float qs[nb], kpc[nb], mfc[nb];
-  apply_action<ARM, TASK>(P, S, F, a, env_offset(P, e), qs, kpc, mfc);
+  int ik_n;
+  apply_action<ARM, TASK>(P, S, F, a, env_offset(P, e), qs, kpc, mfc, ik_n);
 #pragma unroll
   for (int k = 0; k < PIH_NB_MAX; ++k) qtarget[(size_t)PIH_NB_MAX * e + k] = (k < nb) ? qs[k < nb ? k : 0] : 0.0f;
 }
@@ -455,7 +462,7 @@ __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a
 // ------------------------------------------------------------------------------------------------ host side
 using namespace pih;
 
-#define PIH_ALIAS_SLOTS 96
+#define PIH_ALIAS_SLOTS 16
 struct pih_handle {
   pih_config cfg;
   SimParams P;
@@ -470,11 +477,12 @@ struct pih_handle {
   unsigned char* d_done;
   float* d_scene;  // render pre-pass output [n][PIH_SCENE_WORDS], allocated on first pih_render
   float* d_qt;     // joint targets [nb][n] between k_apply_action and k_step_dyn (large batches), allocated on first use
-  int split;       // large batches: step = k_apply_action + k_step_dyn (0: fused k_step; env PIH_SPLIT overrides)
-  // host pointer -> mapped device alias cache of pih_step_host
-  const void* alias_host[PIH_ALIAS_SLOTS];
-  void* alias_dev[PIH_ALIAS_SLOTS];
-  int n_alias, alias_next, no_zero_copy;
+  int split;       // large batches: step = k_apply_action + k_step_dyn (0: fused k_step); pih_config.kernel_family overrides
+  // host buffers bound with pih_host_bind (the caller guarantees their lifetime until pih_host_unbind): base, size, device alias
+  const char* bind_host[PIH_ALIAS_SLOTS];
+  size_t bind_bytes[PIH_ALIAS_SLOTS];
+  char* bind_dev[PIH_ALIAS_SLOTS];
+  int n_bind, no_zero_copy;
   unsigned* d_cta_counter;   // fused step signal: CTAs that have delivered their rows (re-armed by the last one)
 };
 
@@ -485,13 +493,20 @@ static int fail(pih_handle* h, int code, const char* what, cudaError_t ce) {
   return code;
 }
 
-// make the handle's device current (cheap when it already is): launches must go to the device that owns the state
-static int use_device(pih_handle* h) {
-  int cur = -1;
-  if (cudaGetDevice(&cur) == cudaSuccess && cur == h->cfg.device) return PIH_OK;
-  cudaError_t ce = cudaSetDevice(h->cfg.device);
-  return ce == cudaSuccess ? PIH_OK : fail(h, PIH_ERR_CUDA, "cudaSetDevice", ce);
-}
+// Makes the handle's device current for the duration of an entry point (launches must go to the device that owns the
+// state) and restores the caller's current device on return: a library call must not change the caller's device.
+struct DeviceGuard {
+  int prev, dev;
+  bool ok;
+  explicit DeviceGuard(int device) : prev(-1), dev(device), ok(true) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (prev >= 0 && prev != dev) cudaSetDevice(prev); }
+};
+#define USE_DEVICE(h)                                                                  \
+  DeviceGuard guard_((h)->cfg.device);                                                 \
+  if (!guard_.ok) return fail((h), PIH_ERR_CUDA, "cudaSetDevice", cudaGetLastError())
 
 #define FILL_ARM(T, P)                                                                          \
   do {                                                                                          \
@@ -581,12 +596,14 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   // the ur5 variant exists for the peg-in-hole task (utils.py:40-48,70-82); random-fly and the scripted episode are
   // panda tasks (README.md:38, peg_in_hole.py:233), and their ur5 kernels are not instantiated
   if (cfg->arm == PIH_ARM_UR5 && cfg->task != PIH_TASK_PEG_IN_HOLE) return PIH_ERR_INVALID;
+  if (cfg->kernel_family < 0 || cfg->kernel_family > 3 || cfg->host_path < 0 || cfg->host_path > 1) return PIH_ERR_INVALID;
   if (!(cfg->dt > 0.0f) || cfg->solver_iters < 0 || cfg->ik_iters < 0 || !(cfg->solver_residual >= 0.0f)) return PIH_ERR_INVALID;
   // reference assert: task_num == 1 or offset != [0,0,0] (envs/base_env.py:17)
   if (cfg->sub_num > 1 && cfg->offset[0] == 0.0f && cfg->offset[1] == 0.0f && cfg->offset[2] == 0.0f) return PIH_ERR_INVALID;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) return PIH_ERR_CUDA;
-  if (cudaSetDevice(cfg->device) != cudaSuccess) return PIH_ERR_CUDA;
+  DeviceGuard guard_(cfg->device);
+  if (!guard_.ok) return PIH_ERR_CUDA;
   pih_handle* h = new (std::nothrow) pih_handle();
   if (!h) return PIH_ERR_INVALID;
   memset(h, 0, sizeof(*h));
@@ -631,17 +648,13 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   // SM): measured faster than the classic kernels up to 16384 envs for both arms (tools/ws_threshold_probe.py), slower
   // from 24576 envs on, where the classic kernels' one warp per 32 envs fills the schedulers first
   h->ws = (P.n <= 148 * 32 * 4) ? 1 : 0;
-  const char* wse = getenv("PIH_WS");
-  if (wse) h->ws = atoi(wse) ? 1 : 0;
   // measured (tools/split_probe.py): fused 216 / 434 / 781 us against split 196 / 378 / 692 us per step at 65536 /
   // 131072 / 262144 envs; below ~2 waves of the fused kernel the extra launch does not pay (104 vs 106 us at 32768)
   h->split = (P.n >= 49152) ? 1 : 0;
-  const char* spe = getenv("PIH_SPLIT");
-  if (spe) h->split = atoi(spe) ? 1 : 0;
-  const char* nz = getenv("PIH_NO_ZERO_COPY");   // diagnostics: force the staged-copy host path
-  if (nz) h->no_zero_copy = atoi(nz) ? 1 : 0;
-  const char* bs = getenv("PIH_BLOCK");
-  if (bs) { int b = atoi(bs); if (b == 32 || b == 64 || b == 128) h->block = b; }
+  if (cfg->kernel_family == PIH_KERNELS_WARP_SPECIALISED) { h->ws = 1; h->split = 0; }
+  else if (cfg->kernel_family == PIH_KERNELS_FUSED) { h->ws = 0; h->split = 0; }
+  else if (cfg->kernel_family == PIH_KERNELS_SPLIT) { h->ws = 0; h->split = 1; }
+  h->no_zero_copy = cfg->host_path == 1;
   k_init_state<<<(P.n + 127) / 128, 128>>>(P.state, P.n);
   cudaError_t ce = cudaGetLastError();
   if (ce == cudaSuccess) ce = cudaMalloc(&h->d_cta_counter, sizeof(unsigned));
@@ -731,7 +744,7 @@ const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null hand
 
 int pih_reset(pih_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (!h) return PIH_ERR_INVALID;
-  if (cudaSetDevice(h->cfg.device) != cudaSuccess) return fail(h, PIH_ERR_CUDA, "cudaSetDevice", cudaGetLastError());
+  USE_DEVICE(h);
   LAUNCH(k_reset, h, stream, h->P, mask_dev, obs_dev);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_reset launch", ce);
@@ -757,7 +770,7 @@ static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, flo
   if (!h || !action_dev) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "step() before reset()", cudaSuccess);
   if ((uintptr_t)action_dev & (h->P.arm == PIH_ARM_PANDA ? 15 : 7)) return fail(h, PIH_ERR_INVALID, "action rows must be 16-byte (Box(4)) / 8-byte (Box(6)) aligned", cudaSuccess);
-  if (use_device(h)) return PIH_ERR_CUDA;
+  USE_DEVICE(h);
   const StepSignal sig = {flag_dev, flag_value, h->d_cta_counter};
   if (h->ws) { LAUNCH_WS(k_step_ws, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev, sig); }
   else {
@@ -803,24 +816,60 @@ static bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
-// Device alias of a page-locked, device-mapped host buffer (NULL when the buffer is pageable or not mapped).  The
-// answer per host pointer is remembered in a small table: callers cycle through a handful of buffers.
+// Device alias of a page-locked, device-mapped host buffer (NULL when the buffer is pageable or not mapped).
+// Buffers the caller has bound with pih_host_bind (lifetime guaranteed by the caller) resolve from the handle's table;
+// any other pointer is re-queried on EVERY call - a remembered answer could outlive the allocation it described (a
+// freed pinned buffer whose address is reused by a pageable one), and the query costs about a microsecond.
 static void* mapped_alias(pih_handle* h, const void* p) {
   if (!p) return nullptr;
-  for (int i = 0; i < h->n_alias; ++i)
-    if (h->alias_host[i] == p) return h->alias_dev[i];
-  void* d = nullptr;
-  if (is_pinned(p)) {
-    if (cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) { cudaGetLastError(); d = nullptr; }
+  const char* c = static_cast<const char*>(p);
+  for (int i = 0; i < h->n_bind; ++i)
+    if (c >= h->bind_host[i] && c < h->bind_host[i] + h->bind_bytes[i]) return h->bind_dev[i] + (c - h->bind_host[i]);
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type != cudaMemoryTypeHost) return nullptr;
+  return a.devicePointer;   // NULL when the registration is not device-mapped
+}
+
+int pih_host_bind(pih_handle* h, const void* host_ptr, uint64_t bytes) {
+  if (!h || !host_ptr || bytes == 0) return PIH_ERR_INVALID;
+  USE_DEVICE(h);
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host_ptr) != cudaSuccess) { cudaGetLastError(); return fail(h, PIH_ERR_INVALID, "pih_host_bind: not a CUDA-visible host buffer", cudaSuccess); }
+  if (a.type != cudaMemoryTypeHost || !a.devicePointer) return fail(h, PIH_ERR_INVALID, "pih_host_bind: buffer is not page-locked and device-mapped", cudaSuccess);
+  // the whole range must belong to the same mapping: its last byte has to resolve to the matching alias
+  cudaPointerAttributes e;
+  const char* last = static_cast<const char*>(host_ptr) + bytes - 1;
+  if (cudaPointerGetAttributes(&e, last) != cudaSuccess || e.type != cudaMemoryTypeHost ||
+      static_cast<char*>(e.devicePointer) - static_cast<char*>(a.devicePointer) != (ptrdiff_t)(bytes - 1)) {
+    cudaGetLastError();
+    return fail(h, PIH_ERR_INVALID, "pih_host_bind: range exceeds the page-locked allocation", cudaSuccess);
   }
-  const int slot = h->n_alias < PIH_ALIAS_SLOTS ? h->n_alias++ : (h->alias_next++ % PIH_ALIAS_SLOTS);
-  h->alias_host[slot] = p; h->alias_dev[slot] = d;
-  return d;
+  for (int i = 0; i < h->n_bind; ++i)
+    if (h->bind_host[i] == host_ptr) { h->bind_bytes[i] = (size_t)bytes; h->bind_dev[i] = static_cast<char*>(a.devicePointer); return PIH_OK; }
+  if (h->n_bind >= PIH_ALIAS_SLOTS) return fail(h, PIH_ERR_INVALID, "pih_host_bind: table full", cudaSuccess);
+  h->bind_host[h->n_bind] = static_cast<const char*>(host_ptr); h->bind_bytes[h->n_bind] = (size_t)bytes;
+  h->bind_dev[h->n_bind] = static_cast<char*>(a.devicePointer);
+  h->n_bind += 1;
+  return PIH_OK;
+}
+
+int pih_host_unbind(pih_handle* h, const void* host_ptr) {
+  if (!h) return PIH_ERR_INVALID;
+  for (int i = 0; i < h->n_bind; ++i)
+    if (h->bind_host[i] == host_ptr || !host_ptr) {
+      h->n_bind -= 1;
+      h->bind_host[i] = h->bind_host[h->n_bind]; h->bind_bytes[i] = h->bind_bytes[h->n_bind]; h->bind_dev[i] = h->bind_dev[h->n_bind];
+      if (host_ptr) return PIH_OK;
+      --i;
+    }
+  return host_ptr ? PIH_ERR_INVALID : PIH_OK;
 }
 
 int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host, void* stream) {
   if (!h || !action_host) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "step() before reset()", cudaSuccess);
+  USE_DEVICE(h);
   cudaStream_t st = (cudaStream_t)stream;
   size_t n = (size_t)h->P.n, A = (size_t)pih_action_dim(h->P.arm);
   // Zero-copy: when every caller buffer is page-locked and device-mapped, the step kernel reads the actions from and
@@ -865,7 +914,7 @@ int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, floa
 int pih_rollout(pih_handle* h, int32_t steps, float* obs_dev, float* reward_dev, uint8_t* done_dev, unsigned long long* counters_dev, void* stream) {
   if (!h || steps < 0) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "rollout() before reset()", cudaSuccess);
-  if (use_device(h)) return PIH_ERR_CUDA;
+  USE_DEVICE(h);
   if (h->ws) { LAUNCH_WS(k_rollout_ws, h, stream, h->P, (int)steps, obs_dev, reward_dev, done_dev, counters_dev); }
   else if (h->split && h->P.task != PIH_TASK_SCRIPTED) {
     // large batches: the two-kernel step (see k_apply_action), `steps` times; at these sizes a launch is noise
@@ -887,9 +936,15 @@ int pih_rollout(pih_handle* h, int32_t steps, float* obs_dev, float* reward_dev,
   return PIH_OK;
 }
 
+int pih_set_stats(pih_handle* h, unsigned long long* stats_dev) {
+  if (!h) return PIH_ERR_INVALID;
+  h->P.stats = stats_dev;
+  return PIH_OK;
+}
+
 int pih_ik_targets(pih_handle* h, const float* action_dev, float* qtarget_dev, void* stream) {
   if (!h || !action_dev || !qtarget_dev) return PIH_ERR_INVALID;
-  if (use_device(h)) return PIH_ERR_CUDA;
+  USE_DEVICE(h);
   LAUNCH(k_ik, h, stream, h->P, action_dev, qtarget_dev);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_ik launch", ce);
@@ -898,7 +953,7 @@ int pih_ik_targets(pih_handle* h, const float* action_dev, float* qtarget_dev, v
 
 int pih_ee_pose(pih_handle* h, float* pos_dev, float* rot_dev, void* stream) {
   if (!h) return PIH_ERR_INVALID;
-  if (use_device(h)) return PIH_ERR_CUDA;
+  USE_DEVICE(h);
   LAUNCH_ARM(k_ee, h, stream, h->P, pos_dev, rot_dev);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_ee launch", ce);
@@ -908,7 +963,7 @@ int pih_ee_pose(pih_handle* h, float* pos_dev, float* rot_dev, void* stream) {
 int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, void* stream) {
   if (!h || !rgbd_dev || width <= 0 || height <= 0) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "render() before reset()", cudaSuccess);
-  if (use_device(h)) return PIH_ERR_CUDA;
+  USE_DEVICE(h);
   if (!h->d_scene) {
     cudaError_t ce = cudaMalloc(&h->d_scene, (size_t)h->P.n * PIH_SCENE_WORDS * sizeof(float));
     if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "scene allocation", ce);
@@ -938,7 +993,8 @@ int pih_peer_alloc(int32_t device, uint64_t bytes, void** ptr_out, uint8_t handl
   if (!ptr_out || !handle_out || bytes == 0) return PIH_ERR_INVALID;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   cudaIpcMemHandle_t hd;
-  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(ptr_out, (size_t)bytes) != cudaSuccess ||
+  DeviceGuard guard_(device);
+  if (!guard_.ok || cudaMalloc(ptr_out, (size_t)bytes) != cudaSuccess ||
       cudaMemset(*ptr_out, 0, (size_t)bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
       cudaIpcGetMemHandle(&hd, *ptr_out) != cudaSuccess) { cudaGetLastError(); return PIH_ERR_CUDA; }
   memcpy(handle_out, &hd, 64);
@@ -948,7 +1004,8 @@ int pih_peer_open(int32_t device, const uint8_t handle[64], void** ptr_out) {
   if (!ptr_out || !handle) return PIH_ERR_INVALID;
   cudaIpcMemHandle_t hd;
   memcpy(&hd, handle, 64);
-  if (cudaSetDevice(device) != cudaSuccess || cudaIpcOpenMemHandle(ptr_out, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+  DeviceGuard guard_(device);
+  if (!guard_.ok || cudaIpcOpenMemHandle(ptr_out, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
     cudaGetLastError();
     return PIH_ERR_CUDA;
   }
@@ -964,7 +1021,7 @@ int pih_peer_release(void* ptr, int32_t is_owner) {
 int pih_enable_peer(pih_handle* h, int32_t peer_device) {
   if (!h) return PIH_ERR_INVALID;
   if (peer_device == h->cfg.device) return PIH_OK;
-  if (use_device(h)) return PIH_ERR_CUDA;
+  USE_DEVICE(h);
   int can = 0;
   cudaError_t ce = cudaDeviceCanAccessPeer(&can, h->cfg.device, peer_device);
   if (ce != cudaSuccess || !can) return fail(h, PIH_ERR_CUDA, "no peer access to that device", ce);
@@ -975,7 +1032,7 @@ int pih_enable_peer(pih_handle* h, int32_t peer_device) {
 
 int pih_signal_flag(pih_handle* h, uint32_t* flag_dev, uint32_t value, void* stream) {
   if (!h || !flag_dev) return PIH_ERR_INVALID;
-  if (use_device(h)) return PIH_ERR_CUDA;
+  USE_DEVICE(h);
   k_signal_flag<<<1, 1, 0, (cudaStream_t)stream>>>(flag_dev, value);
   cudaError_t ce = cudaGetLastError();
   return ce == cudaSuccess ? PIH_OK : fail(h, PIH_ERR_CUDA, "k_signal_flag launch", ce);
@@ -984,7 +1041,7 @@ int pih_signal_flag(pih_handle* h, uint32_t* flag_dev, uint32_t value, void* str
 int pih_wait_flags(pih_handle* h, const uint32_t* flags_dev, int32_t count, uint32_t value, uint32_t timeout_ms, uint32_t* timed_out_dev,
                    void* stream) {
   if (!h || !flags_dev || !timed_out_dev || count <= 0 || count > 1024) return PIH_ERR_INVALID;
-  if (use_device(h)) return PIH_ERR_CUDA;
+  USE_DEVICE(h);
   k_wait_flags<<<1, ((count + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(flags_dev, (int)count, value, (unsigned long long)timeout_ms * 1000000ull,
                                                                         timed_out_dev);
   cudaError_t ce = cudaGetLastError();
@@ -994,7 +1051,7 @@ int pih_wait_flags(pih_handle* h, const uint32_t* flags_dev, int32_t count, uint
 int pih_grasp_labels(pih_handle* h, int32_t width, int32_t height, float* labels_dev, float* params_dev, void* stream) {
   if (!h || !labels_dev || width <= 0 || height <= 0) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "grasp_labels() before reset()", cudaSuccess);
-  if (use_device(h)) return PIH_ERR_CUDA;
+  USE_DEVICE(h);
   dim3 grid((unsigned)((width * height + 256 * PIH_RENDER_PPT - 1) / (256 * PIH_RENDER_PPT)), (unsigned)h->P.n);
   k_labels<<<grid, 256, 0, (cudaStream_t)stream>>>(h->P, (int)width, (int)height, labels_dev, params_dev);
   cudaError_t ce = cudaGetLastError();
@@ -1014,7 +1071,8 @@ int pih_debug_cta_ns(unsigned long long* out2048) {
 
 int pih_measure_fp32_peak(int device, double* tflops_out) {
   if (!tflops_out) return PIH_ERR_INVALID;
-  if (cudaSetDevice(device) != cudaSuccess) return PIH_ERR_CUDA;
+  DeviceGuard guard_(device);
+  if (!guard_.ok) return PIH_ERR_CUDA;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PIH_ERR_CUDA;
   float* d_out = nullptr;

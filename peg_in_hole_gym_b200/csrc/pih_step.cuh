@@ -309,11 +309,18 @@ template <int ARM, int TASK> PIH_D void reset_env(const SimParams& P, EnvState& 
     S.ppos[2] = (float)PIH_PEG_SPAWN_Z;
     S.pvel[0] = S.pvel[1] = S.pvel[2] = 0.0f;
   } else {
-    float x = fmaf(u[0], 1.4f, -0.7f);
-    float y2 = u[1] * (0.49f - x * x);
-    y2 = y2 > 0.0f ? y2 : 0.0f;
-    float y = sqrtf(y2) * ((u[2] < 0.5f) ? -1.0f : 1.0f);
-    float zz = 0.49f - x * x - y2;
+    // random_pos_in_panda_space (envs/utils.py:97-107): x ~ U(-.7,.7), y = (sqrt(U(0,.49-x^2)) - U(0,.4)) * (+-1), drawn
+    // again while .49 - x^2 - y^2 < 0; z = sqrt(.49 - x^2 - y^2) + 0.2.  Attempt k draws from Philox stream FLY + k.
+    float x = 0.0f, y = 0.0f, zz = 0.49f;
+    for (int k = 0; k < PIH_FLY_MAX_ATTEMPTS; ++k) {
+      float v[4];
+      rng4(P, gid, (unsigned)S.episode, PIH_STREAM_FLY + k, v);
+      const float xk = fmaf(v[0], 1.4f, -0.7f);
+      const float a2 = fmaf(-xk, xk, 0.49f);
+      const float yk = (sqrtf(v[1] * (a2 > 0.0f ? a2 : 0.0f)) - v[2] * 0.4f) * ((v[3] < 0.5f) ? -1.0f : 1.0f);
+      const float rem = fmaf(-yk, yk, a2);
+      if (!(rem < 0.0f)) { x = xk; y = yk; zz = rem; break; }
+    }
     float z = sqrtf(zz > 0.0f ? zz : 0.0f) + 0.2f;
     float ca, sa;
     det_sincos(u[3] * 6.2831855f, sa, ca);
@@ -350,7 +357,8 @@ template <int ARM> PIH_D void observe(const EnvState& S, v3 off, float (&obs)[5]
 // Scripted task: apply_action is `pass` (peg_in_hole.py:30-31); the command comes from the grasp state machine
 // (peg_in_hole.py:39-212).  Returns true when the FSM has reached its final state.
 template <int ARM, int TASK> PIH_D bool apply_action(const SimParams& P, EnvState& S, const FK<ARM>& F, const float* action, v3 off, float* qstar,
-                                           float* kpc, float* mfc) {
+                                           float* kpc, float* mfc, int& ik_n) {
+  ik_n = 0;
   constexpr int nb = ArmDims<ARM>::NB, na = ArmDims<ARM>::NARM;
   const ArmTables& T = c_arm[ARM];
   v3 pee; m3 Ree;
@@ -400,7 +408,7 @@ template <int ARM, int TASK> PIH_D bool apply_action(const SimParams& P, EnvStat
       tgt = mk(res[0], res[1], res[2] + zoff);
       euler_to_quat(0.0f, (float)(-3.141592653589793), yaw_cmd, tq);
       float qik[nb];
-      ik_dls<ARM>(P, F, S.q, tgt, tq, qik);
+      ik_dls<ARM>(P, F, S.q, tgt, tq, qik, ik_n);
 #pragma unroll
       for (int j = 0; j < na && j < 7; ++j) S.mtgt[j] = qik[j];
     }
@@ -431,7 +439,7 @@ template <int ARM, int TASK> PIH_D bool apply_action(const SimParams& P, EnvStat
     tgt = mk(ax, ay, az);
     euler_to_quat(action[3], action[4], action[5], tq);
   }
-  ik_dls<ARM>(P, F, S.q, tgt, tq, qstar);
+  ik_dls<ARM>(P, F, S.q, tgt, tq, qstar, ik_n);
 #pragma unroll
   for (int j = na; j < nb; ++j) qstar[j] = action[3];
   return false;
@@ -476,7 +484,9 @@ template <int ARM, int TASK> __device__ __noinline__ bool step_env(const SimPara
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
   float qstar[nb], kpc[nb], mfc[nb];
-  const bool fsm_done = apply_action<ARM, TASK>(P, S, F, action, off, qstar, kpc, mfc);
+  int ik_n;
+  const bool fsm_done = apply_action<ARM, TASK>(P, S, F, action, off, qstar, kpc, mfc, ik_n);
+  stat_add(P, PIH_STAT_IK_ITERS, (unsigned)ik_n);
   step_back<ARM, TASK>(P, S, F, qstar, kpc, mfc, fsm_done, true, off, gid, obs, reward, done);
   return true;
 }

@@ -23,15 +23,18 @@ TASK_LIST = {
 class LazyInfos:
     """`infos` of the reference is a list of dicts (base_env.py:90); materialising N dicts (or even reading the flags
     word back) per step would cap throughput, so nothing is computed until an element is
-    accessed: then the flags word of the state is read once and dicts are built on demand.  Indexes like the
-    reference's nested lists."""
+    accessed: then the flags word is read once and dicts are built on demand.  The word is SNAPSHOT on the device at the
+    step that produced it (one [N] int32 copy, no D2H), so infos kept from step t still describe step t after later
+    steps, resets or auto-resets - the reference's infos are per-step snapshots too.  Indexes like the reference's
+    nested lists.  `success` is true for the step in which an episode ended in success, also under auto_reset (where the
+    env has already restarted: PIH_FLAG_PREV_SUCCESS); `fault` reports the non-finite guard."""
 
-    def __init__(self, shape, sim=None, flags=None):
-        self._shape, self._sim, self._flags = tuple(shape), sim, flags
+    def __init__(self, shape, flags_dev=None, flags=None):
+        self._shape, self._dev, self._flags = tuple(shape), flags_dev, flags
 
     def _load(self):
         if self._flags is None:
-            self._flags = self._sim.int_word(11).cpu().numpy()
+            self._flags = self._dev.cpu().numpy()
         return self._flags
 
     def __len__(self):
@@ -43,7 +46,7 @@ class LazyInfos:
             n = int(np.prod(self._shape[1:]))
             return LazyInfos(self._shape[1:], flags=flags[i * n:(i + 1) * n])
         f = int(flags[i])
-        return {"success": bool(f & 2), "contact_pairs": (f >> 8) & 0xff}
+        return {"success": bool(f & (2 | 8)), "contact_pairs": (f >> 8) & 0xff, "fault": bool(f & 4)}
 
     def tolist(self):
         return [self[i].tolist() if len(self._shape) > 1 else self[i] for i in range(self._shape[0])]
@@ -97,7 +100,7 @@ class BaseEnv(gym.Env):
     def _pack(self, obs, reward, done):
         shp = self._shape()
         obs, reward, done = obs.view(*shp, -1), reward.view(*shp), done.view(*shp).bool()
-        infos = LazyInfos(shp, sim=self.sim)
+        infos = LazyInfos(shp, flags_dev=self.sim.state[2, :, 3].clone().view(torch.int32))   # word 11 = flags
         if self.as_lists:
             return obs.cpu().numpy().tolist(), reward.cpu().numpy().tolist(), done.cpu().numpy().tolist(), infos.tolist()
         return obs, reward, done, infos

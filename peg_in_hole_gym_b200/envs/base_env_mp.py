@@ -30,7 +30,10 @@ class BaseEnvMp(BaseEnv):
         self.mp_lo, self.mp_hi = lo, hi
         self.mp_num = hi - lo          # clients owned by this rank
         self.sub_num = sub_num
-        super().__init__(client, task, sub_num, offset, args, is_test, _mp_num=max(self.mp_num, 1),
+        if self.mp_num <= 0:
+            raise ValueError(f"mp_num={mp_num} clients cannot be sharded over {ws} ranks: rank {rank} would own none "
+                             "(use mp_num >= world size, or shard=False for a full copy per rank)")
+        super().__init__(client, task, sub_num, offset, args, is_test, _mp_num=self.mp_num,
                          _env_id_base=lo * sub_num, **kwargs)
         self.clients = [self] * self.mp_num
         base_a, base_o = self.action_space, self.observation_space

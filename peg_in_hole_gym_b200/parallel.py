@@ -88,19 +88,35 @@ class PeerLearnerBuffer:
 
     ALIGN = 256
 
-    def __init__(self, sim, rank=None, world_size=None, buf=None):
+    def __init__(self, sim, rank=None, world_size=None, buf=None, counts=None):
         import ctypes as C
         from . import _native as N
         self.sim = sim
         r, ws = world()
         self.rank = r if rank is None else int(rank)
         self.world_size = ws if world_size is None else int(world_size)
-        n, od = sim.n, sim.obs_dim
-        self.n, self.obs_dim = n, od
-        raw = n * od * 4 + n * 4 + n
-        self.per = (raw + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-        self.flag_off = self.world_size * self.per
-        total = self.flag_off + self.ALIGN
+        od = sim.obs_dim
+        self.obs_dim = od
+        # Every rank's slice is laid out from the AGREED per-rank env counts (shard_clients hands out uneven blocks when
+        # mp_num % world_size != 0): one all_gather at construction, prefix offsets from it.  A layout computed from the
+        # local count alone would make ranks disagree about where slices and flag words live.
+        if counts is None:
+            if buf is None and self.world_size > 1:
+                import torch.distributed as dist
+                c = torch.tensor([sim.n], dtype=torch.int64, device=sim.device)
+                cl = [torch.zeros_like(c) for _ in range(self.world_size)]
+                dist.all_gather(cl, c)
+                counts = [int(v.item()) for v in cl]
+            else:
+                counts = [sim.n] * self.world_size
+        self.counts = [int(c) for c in counts]
+        if len(self.counts) != self.world_size or self.counts[self.rank] != sim.n:
+            raise ValueError(f"learner buffer: per-rank env counts {self.counts} do not match this rank's {sim.n} envs")
+        if min(self.counts) <= 0:
+            raise ValueError(f"learner buffer: a rank owns no envs ({self.counts}); use mp_num >= world_size")
+        self.n = sim.n
+        self.offsets, total = self.layout(self.counts, od)
+        self.flag_off = total - self.ALIGN
         self._raw, self._owner = None, False
         if buf is not None:                                   # members of one process share a torch tensor
             self.buf, self.base = buf, buf.data_ptr()
@@ -141,23 +157,32 @@ class PeerLearnerBuffer:
         except Exception:
             pass
 
-    @staticmethod
-    def total_bytes(n, obs_dim, world_size):
-        raw = n * obs_dim * 4 + n * 4 + n
-        per = (raw + PeerLearnerBuffer.ALIGN - 1) // PeerLearnerBuffer.ALIGN * PeerLearnerBuffer.ALIGN
-        return world_size * per + PeerLearnerBuffer.ALIGN
+    @classmethod
+    def layout(cls, counts, obs_dim):
+        """(slice offsets per rank, total bytes): slices [obs n_r*od f32 | reward n_r f32 | done n_r u8] rounded up to ALIGN,
+        then one ALIGN-sized block of flag words."""
+        offs, pos = [], 0
+        for n in counts:
+            offs.append(pos)
+            raw = n * obs_dim * 4 + n * 4 + n
+            pos += (raw + cls.ALIGN - 1) // cls.ALIGN * cls.ALIGN
+        return offs, pos + cls.ALIGN
+
+    @classmethod
+    def total_bytes(cls, n, obs_dim, world_size):
+        return cls.layout([n] * world_size, obs_dim)[1]
 
     def _views(self, r):
-        n, od = self.n, self.obs_dim
-        base = self.buf[r * self.per:(r + 1) * self.per]
+        n, od = self.counts[r], self.obs_dim
+        base = self.buf[self.offsets[r]:]
         obs = base[:n * od * 4].view(torch.float32).view(n, od)
         rew = base[n * od * 4:n * od * 4 + n * 4].view(torch.float32)
         done = base[n * od * 4 + n * 4:n * od * 4 + n * 4 + n]
         return obs, rew, done
 
     def _ptrs(self, r):
-        n, od = self.n, self.obs_dim
-        b = self.base + r * self.per
+        n, od = self.counts[r], self.obs_dim
+        b = self.base + self.offsets[r]
         return b, b + n * od * 4, b + n * od * 4 + n * 4
 
     def _flag_ptr(self, r):
@@ -179,6 +204,7 @@ class PeerLearnerBuffer:
         (views of the learner buffer, valid for work enqueued after this call on the same stream)."""
         from . import _native as N
         sim = self.sim
+        self.timed_out.zero_()          # re-armed per wait: a timeout reported by check() belongs to THIS wait
         rc = sim._L.pih_wait_flags(sim._h, self.base + self.flag_off, self.world_size, self.step_no, int(timeout_ms),
                                    self.timed_out.data_ptr(), sim._stream())
         if rc:
@@ -188,7 +214,8 @@ class PeerLearnerBuffer:
         return self._rows
 
     def check(self):
-        """Host-side: raises if a device-side wait gave up (synchronises the stream)."""
+        """Host-side: raises if the last device-side wait gave up (synchronises the stream).  The rows returned by that
+        wait() are not valid then."""
         v = int(self.timed_out.item())
         if v:
             raise RuntimeError(f"peer gather: rank {v - 1} did not publish step {self.step_no} in time")

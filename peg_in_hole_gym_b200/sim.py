@@ -11,19 +11,59 @@ import torch
 from . import _native as N
 
 
+class HostStepper:
+    """Owner of one set of host buffers bound to a simulator (pih_host_bind / pih_host_unbind): the lifetime contract of
+    the zero-copy host path is this object's lifetime."""
+
+    def __init__(self, sim, action_nps, obs_np, reward_np, done_np):
+        self._sim, self._keep = sim, (list(action_nps), obs_np, reward_np, done_np)
+        self._a = [C.c_void_p(a.ctypes.data) for a in action_nps]
+        self._o, self._r, self._d = (C.c_void_p(x.ctypes.data) for x in (obs_np, reward_np, done_np))
+        self._fn, self._h, self._st = sim._L.pih_step_host, sim._h, C.c_void_p(sim._stream())
+        self._bound = []
+        spans = sorted((a.ctypes.data, a.nbytes) for a in list(action_nps) + [obs_np, reward_np, done_np])
+        merged = []
+        for addr, nb in spans:                                  # views of one page-locked block bind as one range
+            if merged and merged[-1][0] + merged[-1][1] == addr:
+                merged[-1][1] += nb
+            else:
+                merged.append([addr, nb])
+        for addr, nb in merged:
+            if sim._L.pih_host_bind(sim._h, addr, nb) == 0:      # pageable buffers stay unbound (queried per call)
+                self._bound.append(addr)
+
+    def __call__(self, i):
+        rc = self._fn(self._h, self._a[i], self._o, self._r, self._d, self._st)
+        if rc:
+            N.check(rc, self._h, "pih_step_host")
+
+    def close(self):
+        if self._bound and getattr(self._sim, "_h", None):
+            for p in self._bound:
+                self._sim._L.pih_host_unbind(self._sim._h, p)
+        self._bound = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class BatchedSim:
     """num_envs sub-environments resident on one GPU.  State lives in a torch-owned float4-SoA tensor
     ``state[12, N, 4]`` (layout: csrc/pih_constants.h); outputs in ``obs[N,5]``, ``reward[N]``, ``done[N]``."""
 
     def __init__(self, num_envs, task="peg-in-hole", arm="panda", fly_object="banana", sub_num=None, env_id_base=0,
                  offset=(0.0, 0.0, 0.0), dt=1.0 / 240.0, solver_residual=1e-7, solver_iters=50, ik_iters=20, max_steps=0, auto_reset=False,
-                 action_frame_env=False, device=None, seed=0):
+                 action_frame_env=False, device=None, seed=0, kernel_family="auto", host_path=0):
         L = N.lib()
         if not torch.cuda.is_available():
             raise N.PihError("peg_in_hole_gym_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
         self.cfg = N.make_config(num_envs, task, arm, fly_object, sub_num, env_id_base, offset, dt, solver_residual,
-                                 solver_iters, ik_iters, max_steps, auto_reset, action_frame_env, self.device.index, seed)
+                                 solver_iters, ik_iters, max_steps, auto_reset, action_frame_env, self.device.index, seed,
+                                 kernel_family, host_path)
         self.n = int(num_envs)
         self.action_dim = L.pih_action_dim(self.cfg.arm)
         self.obs_dim = L.pih_obs_dim()
@@ -88,19 +128,11 @@ class BatchedSim:
             N.check(rc, self._h, "pih_step_host")
 
     def host_stepper(self, action_nps, obs_np, reward_np, done_np):
-        """Binds pih_step_host to fixed host buffers once (addresses resolved up front) and returns ``step(i)`` which
-        steps with ``action_nps[i]``: the per-call Python work is one ctypes call.  With page-locked buffers
-        (``pinned_host_buffers``) the library runs its zero-copy path."""
-        a_ptrs = [C.c_void_p(a.ctypes.data) for a in action_nps]
-        o, r, d = C.c_void_p(obs_np.ctypes.data), C.c_void_p(reward_np.ctypes.data), C.c_void_p(done_np.ctypes.data)
-        fn, h, st = self._L.pih_step_host, self._h, C.c_void_p(self._stream())
-        keep = (action_nps, obs_np, reward_np, done_np)
-
-        def step(i, _keep=keep):
-            rc = fn(h, a_ptrs[i], o, r, d, st)
-            if rc:
-                N.check(rc, h, "pih_step_host")
-        return step
+        """Binds pih_step_host to fixed host buffers once and returns a callable ``step(i)`` which steps with
+        ``action_nps[i]``: the per-call Python work is one ctypes call.  With page-locked buffers
+        (``pinned_host_buffers``) the library runs its zero-copy path; the stepper keeps the buffers alive and bound
+        (pih_host_bind) for exactly as long as it lives."""
+        return HostStepper(self, action_nps, obs_np, reward_np, done_np)
 
     def pinned_host_buffers(self, n_action_buffers=1):
         """Page-locked numpy views for the host-buffer call: `n_action_buffers` action arrays [N, A] and ONE block laid
@@ -123,6 +155,15 @@ class BatchedSim:
         N.check(self._L.pih_rollout(self._h, int(steps), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
                                     self.counters.data_ptr() if count else None, self._stream()), self._h, "pih_rollout")
         return self.obs, self.reward, self.done
+
+    def stats(self, enable=True):
+        """Execution counters (pih_set_stats): returns the zeroed int64[8] tensor the kernels add to; ``enable=False`` detaches."""
+        if not enable:
+            self._L.pih_set_stats(self._h, None)
+            return None
+        self._stats = torch.zeros(8, dtype=torch.int64, device=self.device)
+        self._L.pih_set_stats(self._h, self._stats.data_ptr())
+        return self._stats
 
     def ik_targets(self, action):
         a = torch.as_tensor(action, dtype=torch.float32).to(self.device).contiguous()

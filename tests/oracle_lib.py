@@ -16,7 +16,7 @@ class PihConfig(C.Structure):
                 ("sub_num", C.c_int32), ("env_id_base", C.c_int32), ("offset", C.c_float * 3), ("dt", C.c_float), ("solver_residual", C.c_float),
                 ("solver_iters", C.c_int32), ("ik_iters", C.c_int32), ("max_steps", C.c_int32),
                 ("auto_reset", C.c_int32), ("action_frame_env", C.c_int32), ("device", C.c_int32),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("kernel_family", C.c_int32), ("host_path", C.c_int32)]
 
 
 def make_config(num_envs, task=0, arm=0, fly_object=0, sub_num=None, env_id_base=0, offset=(0.0, 0.0, 0.0),

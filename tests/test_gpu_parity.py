@@ -24,6 +24,7 @@ def _sim(n, **kw):
 def _pair(n, arm="panda", task="peg-in-hole", use_double=False, **kw):
     sim = _sim(n, arm=arm, task=task, **kw)
     okw = dict(kw)
+    okw.pop("kernel_family", None); okw.pop("host_path", None)
     okw["auto_reset"] = int(okw.get("auto_reset", False))
     okw["action_frame_env"] = int(okw.get("action_frame_env", False))
     if "fly_object" in okw:
@@ -256,14 +257,15 @@ def test_step_host_path_equals_device_path():
     assert np.array_equal(sim_a.done.cpu().numpy(), pdone)
 
 
-@pytest.mark.parametrize("ws", ["0", "1"])
-def test_zero_copy_host_path_with_frozen_envs_and_fresh_buffers(monkeypatch, ws):
+@pytest.mark.parametrize("family", ["fused", "ws", "split"])
+def test_zero_copy_host_path_with_frozen_envs_and_fresh_buffers(family):
     """pih_step_host on page-locked buffers lets the kernel read actions from / write results to host memory.  Done
     envs are frozen (base_env.py:61-71): their outputs are re-emitted from the frozen state, so handing in FRESH output
-    buffers every step still returns the last outputs.  Checked against the oracle for both kernel families."""
-    monkeypatch.setenv("PIH_WS", ws)
+    buffers every step still returns the last outputs.  Checked against the oracle for every kernel family.  The buffers
+    are NOT bound (pih_host_bind), so the library re-queries the driver for their device aliases on every call - a
+    stale alias of a freed buffer can never be used."""
     n = 100
-    sim, orc = _pair(n, offset=(2.0, 3.0, 0.0), seed=21, max_steps=6, auto_reset=False)
+    sim, orc = _pair(n, offset=(2.0, 3.0, 0.0), seed=21, max_steps=6, auto_reset=False, kernel_family=family)
     sim.reset(); orc.reset()
     acts = _random_actions(n, 4, 12, sim.env_offsets().numpy(), 5)
     for t, a in enumerate(acts):
@@ -539,33 +541,122 @@ def test_randomised_states_fuzz_bit_exact(arm, task, fly):
 
 @pytest.mark.parametrize("arm,task", [("panda", "peg-in-hole"), ("ur5", "peg-in-hole"), ("panda", "random-fly"),
                                       ("panda", "peg-in-hole-scripted")])
-def test_classic_and_warp_specialised_kernels_agree(arm, task, monkeypatch):
-    """Small batches run the warp-specialised kernels (k_step_ws / k_rollout_ws: apply_action and the dynamics
-    prologue in two warps), large ones the classic single-warp kernels.  Both must give the oracle's bits."""
+def test_all_kernel_families_agree_with_the_oracle(arm, task):
+    """Three kernel families compute one env.step: the warp-specialised small-batch kernels (k_step_ws / k_rollout_ws),
+    the fused thread-per-env kernels (k_step / k_rollout) and the split pair k_apply_action + k_step_dyn that batches
+    >= 49152 envs (BASELINE config 5) run.  pih_config.kernel_family forces each of them at a test-sized batch; all
+    must give the oracle's bits, for pih_step with EXTERNAL actions and for pih_rollout.  (The scripted task has no
+    split form: its state machine lives in apply_action.)"""
     from peg_in_hole_gym_b200.sim import BatchedSim
     n = 100                                              # not a multiple of 32: padding lanes in the last CTA
     kw = dict(task=task, arm=arm, offset=(2.0, 3.0, 0.0), seed=6, max_steps=0 if "scripted" in task else 30,
               auto_reset="scripted" not in task, dt=1.0 / 120.0 if task == "random-fly" else 1.0 / 240.0)
-    sims = {}
-    for ws in ("0", "1"):
-        monkeypatch.setenv("PIH_WS", ws)
-        sims[ws] = BatchedSim(n, device=0, **kw)
-        sims[ws].reset()
+    families = ["ws", "fused"] + ([] if "scripted" in task else ["split"])
+    sims = {f: BatchedSim(n, device=0, kernel_family=f, **kw) for f in families}
+    for sm in sims.values():
+        sm.reset()
     orc = ol.Oracle(ol.make_config(n, task={"peg-in-hole": 0, "random-fly": 1, "peg-in-hole-scripted": 2}[task],
                                    arm={"panda": 0, "ur5": 1}[arm], offset=kw["offset"], seed=6, max_steps=kw["max_steps"],
                                    auto_reset=int(kw["auto_reset"]), dt=kw["dt"]))
     orc.reset()
-    acts = _random_actions(n, 4 if arm == "panda" else 6, 45, sims["0"].env_offsets().numpy(), 9)
-    for a in acts:                                       # per-step launches
-        for sm in sims.values():
-            sm.step(torch.from_numpy(a).cuda())
-        orc.step(a)
+    acts = _random_actions(n, 4 if arm == "panda" else 6, 45, sims["ws"].env_offsets().numpy(), 9)
+    for t, a in enumerate(acts):                         # per-step launches with external actions
+        c = orc.step(a)
+        for f, sm in sims.items():
+            g = sm.step(torch.from_numpy(a).cuda())
+            assert np.array_equal(g[0].cpu().numpy(), c[0]) and np.array_equal(g[1].cpu().numpy(), c[1]), (f, t)
+            assert np.array_equal(g[2].cpu().numpy(), c[2]), (f, t)
+    for sm in sims.values():
+        _assert_state_equal(sm, orc)
     for sm in sims.values():                             # then the rollout kernels
         sm.rollout(70)
     orc.rollout(70)
-    assert torch.equal(sims["0"].state, sims["1"].state)
-    assert torch.equal(sims["0"].obs, sims["1"].obs) and torch.equal(sims["0"].done, sims["1"].done)
-    _assert_state_equal(sims["1"], orc)
+    for f, sm in sims.items():
+        _assert_state_equal(sm, orc)
+        assert np.array_equal(sm.obs.cpu().numpy(), orc.obs), f
+
+
+def test_config5_size_panda_peg_split_kernels():
+    """BASELINE config 5's per-GPU shape: panda peg-in-hole at 65536 envs on one GPU, where pih_create picks the split
+    pair k_apply_action<panda, peg> + k_step_dyn<panda, peg> by itself.  pih_step with external actions and pih_rollout,
+    determinism across launch partitions, invariants, and an oracle check on a slice with the same global env ids."""
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    n, m = 65536, 128
+    kw = dict(offset=(2.0, 3.0, 0.0), seed=55, max_steps=40, auto_reset=True)
+    a = BatchedSim(n, device=0, **kw); a.reset()
+    orc = ol.Oracle(ol.make_config(m, sub_num=n, offset=kw["offset"], seed=55, max_steps=40, auto_reset=1)); orc.reset()
+    offs = torch.zeros(n, 4, device="cuda")
+    offs[:, :3] = a.env_offsets().cuda()
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    for t in range(50):                                  # crosses one auto-reset
+        act = (torch.rand(n, 4, device="cuda", generator=g) * 2 - 1) + offs
+        go, gr, gd = a.step(act)
+        co, cr, cd = orc.step(act[:m].cpu().numpy())
+        assert np.array_equal(go[:m].cpu().numpy(), co) and np.array_equal(gr[:m].cpu().numpy(), cr), t
+        assert np.array_equal(gd[:m].cpu().numpy(), cd), t
+    a.rollout(60); orc.rollout(60)
+    st = a.state.cpu().numpy()
+    assert np.array_equal(st[:, :m], orc.get_state())
+    assert np.isfinite(st).all()
+    assert np.allclose(np.linalg.norm(ol.state_field(st, ol.S_PQUAT, 4), axis=1), 1.0, atol=1e-5)
+    assert (ol.state_int(st, 10) == 2).all() and int(a.counters[0].item()) == n * 60
+    b = BatchedSim(n, device=0, kernel_family="fused", **kw); b.reset()     # the fused kernel on the same batch
+    g.manual_seed(5)
+    for t in range(50):
+        b.step((torch.rand(n, 4, device="cuda", generator=g) * 2 - 1) + offs)
+    b.rollout(25); b.rollout(35)
+    assert torch.equal(a.state, b.state)
+
+
+def test_nonfinite_state_trips_the_fault_guard_and_resets():
+    """a non-finite word in an env's state must not live on in HBM.  NaN / Inf are injected into
+    different state words of some envs of BOTH engines; after one step those envs are re-initialised (new episode),
+    reported done with reward 0 and carry PIH_FLAG_FAULT; every other env is untouched; afterwards the engines keep
+    agreeing bit for bit.  Exercised for every kernel family, with and without auto_reset."""
+    n = 96
+    for family, auto in (("ws", True), ("fused", False), ("split", True)):
+        sim, orc = _pair(n, offset=(2.0, 3.0, 0.0), seed=14, max_steps=50, auto_reset=auto, kernel_family=family)
+        acts = _random_actions(n, 4, 30, sim.env_offsets().numpy(), 3)
+        _run_compare(sim, orc, acts[:10])
+        w = orc.get_state()
+        flat = np.ascontiguousarray(w.transpose(1, 0, 2)).reshape(n, -1)
+        bad = np.arange(3, n, 7)
+        words = [ol.S_Q + 2, ol.S_QD + 5, ol.S_PPOS + 1, ol.S_PQUAT + 3, ol.S_PVEL, ol.S_PANG + 2]
+        for k, e in enumerate(bad):
+            wd = words[k % len(words)]
+            flat[e, wd] = np.nan if (k % 2 == 0 or wd == ol.S_QD + 5) else np.inf   # (an infinite joint RATE alone is clamped to 100)
+        w2 = np.ascontiguousarray(flat.reshape(n, -1, 4).transpose(1, 0, 2)).astype(np.float32)
+        orc.set_state(w2); sim.state.copy_(torch.from_numpy(w2))
+        stats = sim.stats()
+        go, gr, gd = sim.step(torch.from_numpy(acts[10]).cuda())
+        co, cr, cd = orc.step(acts[10])
+        assert np.array_equal(gd.cpu().numpy(), cd) and np.array_equal(gr.cpu().numpy(), cr)
+        assert np.array_equal(go.cpu().numpy(), co)
+        flags = sim.int_word(11).cpu().numpy()
+        assert (flags[bad] & 4).all() and gd.cpu().numpy()[bad].all() and (gr.cpu().numpy()[bad] == 0).all()
+        ok = np.setdiff1d(np.arange(n), bad)
+        assert not (flags[ok] & 4).any()
+        assert int(stats[6].item()) == len(bad) and int(stats[0].item()) == n
+        assert np.isfinite(sim.state.cpu().numpy()).all()
+        _assert_state_equal(sim, orc)
+        sim.stats(False)
+        _run_compare(sim, orc, acts[11:], reset=False)
+
+
+def test_execution_counters():
+    """pih_set_stats: the counters behind the bench line's executed-iteration figures."""
+    n = 256
+    sim, orc = _pair(n, offset=(2.0, 3.0, 0.0), seed=2, max_steps=200, auto_reset=True)
+    sim.reset()
+    sim.rollout(40, count=False)
+    st = sim.stats()
+    sim.rollout(25, count=False)
+    torch.cuda.synchronize()
+    v = st.cpu().numpy()
+    assert v[0] == n * 25
+    assert 0 < v[1] <= 20 * v[0] and v[3] >= v[0] and v[3] <= 50 * v[0] and v[7] <= 50
+    assert v[2] >= 9 * v[0]                          # at least the 9 motor rows once per env-step
+    assert v[6] == 0
 
 
 @pytest.mark.parametrize("n,arm,task,fly,dt", [(16384, "ur5", "peg-in-hole", "banana", 1.0 / 240.0),      # BASELINE config 3

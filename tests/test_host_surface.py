@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     from peg_in_hole_gym_b200 import _native
     assert set(_native.EXPORTS) == declared
     LL = _native.lib()
-    assert LL.pih_abi_version() == 1 and LL.pih_state_words() == 48 and LL.pih_obs_dim() == 5
+    assert LL.pih_abi_version() == 2 and LL.pih_state_words() == 48 and LL.pih_obs_dim() == 5
     assert LL.pih_action_dim(0) == 4 and LL.pih_action_dim(1) == 6 and LL.pih_action_dim(7) < 0
 
 
@@ -113,6 +113,17 @@ def test_shard_clients_partition():
         assert all(got[i][1] == got[i + 1][0] for i in range(ws - 1))
         sizes = [b - a for a, b in got]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_peer_learner_buffer_layout_is_agreed_from_all_ranks_counts():
+    """uneven shards (mp_num % world_size != 0) must not make ranks disagree about slice / flag offsets: the
+    layout is a pure function of the all-gathered per-rank counts."""
+    from peg_in_hole_gym_b200.parallel import PeerLearnerBuffer as PLB, shard_clients
+    counts = [(b - a) * 6 for a, b in (shard_clients(5, r, 2) for r in range(2))]         # 18 and 12 envs
+    offs, total = PLB.layout(counts, 5)
+    assert counts == [18, 12] and offs[0] == 0 and offs[1] % PLB.ALIGN == 0
+    assert offs[1] >= 18 * 25 and total - PLB.ALIGN >= offs[1] + 12 * 25                   # slices do not overlap each other or the flags
+    assert PLB.total_bytes(160, 5, 2) == PLB.layout([160, 160], 5)[1]
 
 
 def _gloo_worker(rank, world, port, q):
