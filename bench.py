@@ -40,13 +40,21 @@ SEED = 0
 # algorithmic cost per env-step (SURVEY.md 8d formula)
 BYTES_PER_ENV_STEP = 2 * 192 + 16 + 20 + 4 + 1   # float4-SoA state read+write (12 slots), action, obs, reward, done
 FLOPS_BULLET_DEFAULT = 2.2e5                       # I_ik=20, I_pgs=50, n=9, R=33
-NCU_EXECUTED_FLOPS_PER_ENV_STEP = 5.11e4          # ncu: (2*FFMA + FMUL + FADD thread-instructions) per launch / 4096 envs (profiles/r01_kstep_ws_ncu_full_v3.csv)
-NCU_TRAFFIC_BYTES = 950272                          # k_step_ws<panda>, 4096 envs: DRAM read 950 KB + write 0 B per launch (profiles/r01_kstep_ws_ncu_full_v3.csv)
+# ncu figures are properties of ONE kernel build at ONE batch shape: keyed by (kernel, arm, task, envs); other configs
+# report null (profiles/README.md lists the captures they come from)
+NCU_CAPTURES = {
+    ("pih::k_step_ws", "panda", "peg-in-hole", 4096): {
+        "traffic_bytes": 950272,             # dram__bytes_read.sum + dram__bytes_write.sum per launch
+        "executed_flops_per_env_step": 5.11e4,   # (2*FFMA + FMUL + FADD thread-instructions) per launch / 4096 envs
+        "source": "profiles/r01_kstep_ws_ncu_full_v3.csv"},
+}
 
 
-def flops_per_env_step(n=9, na=7, i_ik=20, i_pgs=50, rows=17):
-    """SURVEY.md 8(d) formula with the parameters this build runs (R = 9 motors + 2 finger limits + 2 contacts x 3)."""
-    return 70 * n + i_ik * (174 * na + 200) + 430 * n + 250 * n * rows + 70 * rows * i_pgs + 2500
+def flops_per_env_step(n=9, na=7, i_ik=20.0, row_iters=17 * 50.0, rows=17.0):
+    """SURVEY.md 8(d) formula: 70n [FK] + I_ik (174 n_a + 200) [IK] + 430n [ABA] + 250 n R [row responses] +
+    70 (R I_pgs) [PGS sweeps] + 2500.  Defaults = the upper bound this build may run (20 IK iterations, 50 sweeps over
+    R = 17 rows); bench.py also evaluates it with the iteration counts the kernels actually executed (pih_set_stats)."""
+    return 70 * n + i_ik * (174 * na + 200) + 430 * n + 250 * n * rows + 70 * row_iters + 2500
 
 
 def measured_peaks():
@@ -145,6 +153,98 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def coprime_stride(nb):
+    """A stride near nb * 0.618 that is coprime with nb: visiting batch (i * stride) % nb spreads any window of consecutive
+    visits evenly over the batches (and so over the episode phases the batches were pre-rolled to)."""
+    from math import gcd
+    s = max(1, int(round(nb * 0.6180339887)))
+    while gcd(s, nb) != 1:
+        s += 1
+    return s
+
+
+def timed_steps(fn, k, barrier, torch):
+    """K calls of fn(i) inside one CUDA-event pair on the current stream, bracketed by barrier + synchronize."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(k):
+        fn(i)
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def config5_sweep(args, rank, world, local, dev, reduce_max, barrier):
+    """BASELINE config 5: panda peg-in-hole, 2^17..2^20 envs in total sharded evenly over the ranks, per-step gather of the
+    (obs5, reward, done) rows to rank 0 off / fused peer write / NCCL collective.  Returns the table for `extra`."""
+    import torch
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    from peg_in_hole_gym_b200.parallel import PeerLearnerBuffer, gather_rows_to_rank0, pack_rows
+    out = []
+    steps, warm = 24, 6
+    for total in (1 << 17, 1 << 18, 1 << 19, 1 << 20):
+        n = total // world
+        sim = BatchedSim(n, sub_num=total, env_id_base=rank * n, offset=OFFSET, seed=SEED, max_steps=MAX_STEPS, auto_reset=True, device=local)
+        sim.reset()
+        sim.rollout(8, count=False)
+        offs = torch.zeros(n, 4, device=dev)
+        offs[:, :3] = sim.env_offsets_device()
+        g = torch.Generator(device=dev); g.manual_seed(99 + rank)
+        ring = [((torch.rand(n, 4, device=dev, generator=g) * 2 - 1) + offs).contiguous() for _ in range(6)]
+        peer = PeerLearnerBuffer(sim)
+        row = {"total_envs": total, "envs_per_gpu": n}
+        for mode in ("none", "peer", "nccl"):
+            def one(i, mode=mode):
+                a = ring[i % len(ring)]
+                if mode == "peer":
+                    peer.step(a, wait_prev=(rank == 0))
+                else:
+                    sim.step(a)
+                    if mode == "nccl":
+                        gather_rows_to_rank0(pack_rows(sim.obs, sim.reward, sim.done.float()), counts=[n] * world)
+            for i in range(warm):
+                one(i)
+            ms = timed_steps(one, steps, barrier, torch)
+            if mode == "peer" and rank == 0:
+                peer.wait(); peer.check()
+            ms = reduce_max(ms)
+            row[mode] = {"us_per_step": 1e3 * ms / steps, "env_steps_per_s": total * steps / (ms * 1e-3)}
+        for mode in ("peer", "nccl"):
+            row[mode]["gather_cost_us"] = row[mode]["us_per_step"] - row["none"]["us_per_step"]
+        out.append(row)
+        barrier()
+        peer.close(); sim.close()
+        del ring, offs, sim, peer
+        torch.cuda.empty_cache()
+    return out
+
+
+def contact_rich_probe(n, local, torch, barrier):
+    """The regime a trained policy lives in: the scripted grasp episode at n envs - engine steps with
+    the peg held between the fingers (finger<->peg rows couple the arm and free-body islands) beside the contact-free
+    approach phase, microseconds per engine step of the rollout kernel."""
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    sim = BatchedSim(n, task="peg-in-hole-scripted", sub_num=n, offset=OFFSET, seed=SEED, device=local)
+    sim.reset()
+    out = {}
+    sim.rollout(100, count=False)                                       # state 1: moving over the peg, no contacts
+    out["approach_us_per_step"] = 1e3 * timed_steps(lambda i: sim.rollout(25, count=False), 4, barrier, torch) / 100
+    sim.rollout(1140, count=False)                                      # -> step 1340: state 4, lifting the grasped peg
+    st = sim.stats()
+    out["grasp_us_per_step"] = 1e3 * timed_steps(lambda i: sim.rollout(25, count=False), 4, barrier, torch) / 100
+    v = st.cpu().numpy().astype(float)
+    sim.stats(False)
+    flags = sim.int_word(11)
+    out["grasp_envs_with_finger_contact_frac"] = float((((flags >> 8) & 12) != 0).float().mean().item())
+    out["grasp_mean_contacts"] = v[4] / max(v[0], 1.0)
+    out["grasp_mean_pgs_iters"] = v[3] / max(v[0], 1.0)
+    out["ratio"] = out["grasp_us_per_step"] / out["approach_us_per_step"]
+    out["envs"] = n
+    sim.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,12 +254,14 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--arm", default="panda")
     ap.add_argument("--task", default="peg-in-hole")
-    ap.add_argument("--gather", nargs="?", const="nccl", default=None, choices=["nccl", "peer"],
+    ap.add_argument("--gather", default=None, choices=["none", "nccl", "peer"],
                     help="every step all ranks deliver their (obs,reward,done) rows to rank 0: 'nccl' = pack + gather collective; "
-                         "'peer' = the step kernel stores them into rank 0's buffer over NVLink peer memory and signals a flag")
+                         "'peer' = the step kernel stores them into rank 0's buffer over NVLink peer memory and signals a flag "
+                         "(default with more than one GPU); 'none' = independent ranks")
     ap.add_argument("--l2", choices=["rotate", "flush"], default="rotate",
                     help="rotate: inputs larger than L2 (many independent batches round-robin); flush: one batch, L2 flushed between steps")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="skip the config-5 sweep that follows the headline when --gpus > 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -177,17 +279,22 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    gather = args.gather or ("peer" if world > 1 else "none")
+    if world == 1:
+        gather = "none"
     n = args.envs_per_gpu
     adim = 4 if args.arm == "panda" else 6
     dt_sim = 1.0 / 120.0 if args.task == "random-fly" else 1.0 / 240.0
     # L2 policy.  "rotate" (default): inputs larger than L2 - B independent batches of n sub-envs (state + actions +
-    # outputs > 160 MB in total, L2 is 126 MB) are visited round-robin, so every launch reads its state and actions from
-    # HBM while the code stays hot, as in a real rollout; each batch is pre-rolled to a different phase of the 200-step
-    # episode so that the timed window covers all phases evenly.  "flush": one batch, L2 flushed between steps.
+    # outputs > 160 MB in total, L2 is 126 MB), so every launch reads its state and actions from HBM while the code stays
+    # hot, as in a real rollout.  Batch b is pre-rolled to phase b*200/B of the 200-step episode and the batches are
+    # visited with a stride coprime to B, so ANY window of consecutive steps - the driver's 20 as well as 4000 - samples
+    # the episode phases evenly.  "flush": one batch, L2 flushed between steps.
     bytes_per_batch = n * (192 + adim * 4 + 25)
     nb_batches = 1 if args.l2 == "flush" else max(2, -(-160_000_000 // bytes_per_batch))
+    stride = coprime_stride(nb_batches)
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
-    sims, acts = [], []
+    sims = []
     for b in range(nb_batches):
         sm = BatchedSim(n, task=args.task, arm=args.arm, sub_num=n, env_id_base=(rank * nb_batches + b) * n, offset=OFFSET, dt=dt_sim,
                         seed=SEED, max_steps=MAX_STEPS, auto_reset=True, device=local)
@@ -196,17 +303,16 @@ def main():
             sm.rollout((b * MAX_STEPS) // nb_batches, count=False)
         sims.append(sm)
     sim = sims[0]
-    offs = sim.env_offsets().to(dev)
+    offs = sim.env_offsets_device()
     # synthetic actions resident in HBM: U[-1,1]^A centred on each env origin.  One ring of 64 i.i.d. batches shared by
-    # all env batches (the offset layout repeats per batch); batch b reads ring[(visit * 7 + b * 13) % 64], so no batch
-    # sees a short repeating action sequence (cycling a handful of fixed targets drives the arms into their limits).
+    # all env batches (the offset layout repeats per batch); visit v of batch b reads ring[(v * 7 + b * 13) % 64], so no
+    # batch sees a short repeating action sequence (cycling a handful of fixed targets drives the arms into their limits).
     n_act = 64
     ring = []
     for _ in range(n_act):
         a = torch.rand(n, adim, device=dev, generator=g) * 2 - 1
         a[:, :3] += offs
         ring.append(a.contiguous())
-    acts = None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.l2 == "flush" else None
     L = _native.lib()
     peak_tf = None
@@ -216,15 +322,22 @@ def main():
         if L.pih_measure_fp32_peak(local, C.byref(v)) == 0:
             peak_tf = v.value
 
-    peer = PeerLearnerBuffer(sims[0]) if (args.gather == "peer" and world > 1) else None
+    peer = PeerLearnerBuffer(sims[0]) if gather == "peer" else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def one(i, timed):
-        b = i % nb_batches
+    def reduce_max(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def one(i, timed=None):
+        b = (i * stride) % nb_batches
         sm = sims[b]
         if flush is not None:
             flush.zero_()
@@ -232,18 +345,18 @@ def main():
             timed[0].record()
         a = ring[((i // nb_batches) * 7 + b * 13) % n_act]
         if peer is not None:
-            peer.step(a, sm)              # outputs go straight into rank 0's learner buffer, then the flag
-            if rank == 0:
-                peer.wait()
+            # outputs go straight into rank 0's learner buffer, then the flag; rank 0's kernel first waits for the
+            # previous step's rows of every rank (the consumer's wait, folded into its next launch)
+            peer.step(a, sm, wait_prev=(rank == 0))
         else:
             sm.step(a)
-            if args.gather == "nccl" and world > 1:
+            if gather == "nccl":
                 gather_rows_to_rank0(pack_rows(sm.obs, sm.reward, sm.done.float()), counts=[n] * world)
         if timed is not None:
             timed[1].record()
 
     for i in range(max(args.warmup, 3)):
-        one(i, None)
+        one(i)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if args.l2 == "flush":
@@ -251,24 +364,35 @@ def main():
         barrier()
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
-            one(i, evs[i])
+            one(args.warmup + i, evs[i])
         barrier()
         t_wall = time.perf_counter() - t_wall0
         dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     else:
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
         t_wall0 = time.perf_counter()
-        ev0.record()
-        for i in range(args.steps):
-            one(args.warmup + i, None)
-        ev1.record()
-        barrier()
+        dev_ms = timed_steps(lambda i: one(args.warmup + i), args.steps, barrier, torch)
         t_wall = time.perf_counter() - t_wall0
-        dev_ms = ev0.elapsed_time(ev1)
     if peer is not None and rank == 0:
+        peer.wait()       # the last step's rows
         peer.check()      # no device-side wait may have timed out
     clocks = sampler.stop() if sampler else None
+
+    # what the kernels actually executed (pih_set_stats), over one visit of every episode phase: NOT inside the timed region
+    stat_acc = np.zeros(8)
+    n_stat = min(nb_batches, 64)
+    for k in range(n_stat):
+        sm = sims[(k * stride) % nb_batches]
+        st = sm.stats()
+        sm.step(ring[k % n_act])
+        stat_acc[:7] += st.cpu().numpy()[:7]
+        stat_acc[7] = max(stat_acc[7], float(st[7].item()))
+        sm.stats(False)
+    es = max(stat_acc[0], 1.0)
+    executed = {"ik_iters_mean": stat_acc[1] / es, "pgs_iters_mean": stat_acc[3] / es, "pgs_iters_max": stat_acc[7],
+                "pgs_row_iters_mean": stat_acc[2] / es, "contacts_mean": stat_acc[4] / es, "limit_rows_mean": stat_acc[5] / es,
+                "faults": stat_acc[6], "env_steps_sampled": stat_acc[0]}
+    rows_mean = (9 if args.arm == "panda" else 6) + executed["limit_rows_mean"] + 3 * executed["contacts_mean"]
+
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # single-launch rollout (in-kernel Philox actions); first launch of the kernel is a warm-up (local-memory resize)
     sim.rollout(2, count=False)
@@ -278,13 +402,11 @@ def main():
     e1.record()
     barrier()
     roll_ms = e0.elapsed_time(e1)
-    # e2e: host buffers through pih_step_host
-    # e2e: the host-buffer plugin call (pih_step_host) with page-locked host buffers: every step copies that step's actions
-    # H2D, runs the step, and reads (obs, reward, done) back D2H before returning
+    # e2e: the host-buffer plugin call (pih_step_host) with page-locked host buffers: every step the kernel reads that
+    # step's actions from host memory and writes (obs, reward, done) back to host memory, then the host reads the result.
     # Every step gets its OWN i.i.d. action batch (action_space.sample() per step, README.md:48), pre-generated into
     # page-locked host memory: a short repeating action sequence on one batch is a different workload (its net
-    # displacement per period accumulates and drives the arms into the table and their joint limits).  The results land
-    # in one page-locked block [obs | reward | done] that the host reads after every step.
+    # displacement per period accumulates and drives the arms into the table and their joint limits).
     e2e_steps = min(args.steps, 2000)
     e2e_warm = 20
     h_acts, obs_h, rew_h, done_h = sim.pinned_host_buffers(e2e_steps + e2e_warm)
@@ -304,12 +426,11 @@ def main():
         chk += float(rew_h[0]) + float(done_h[-1])      # the host consumes the step's result before the next action
     barrier()
     e2e_s = time.perf_counter() - t0
+    host_step.close()
 
     # the same loop through the staged path (H2D copy, step, one D2H copy), for comparison with the zero-copy call
-    os.environ["PIH_NO_ZERO_COPY"] = "1"
     sim_st = BatchedSim(n, task=args.task, arm=args.arm, sub_num=n, env_id_base=rank * nb_batches * n, offset=OFFSET, dt=dt_sim,
-                        seed=SEED, max_steps=MAX_STEPS, auto_reset=True, device=local)
-    del os.environ["PIH_NO_ZERO_COPY"]
+                        seed=SEED, max_steps=MAX_STEPS, auto_reset=True, device=local, host_path=1)
     sim_st.reset()
     st_steps = min(e2e_steps, 400)
     st_step = sim_st.host_stepper(h_acts, obs_h, rew_h, done_h)
@@ -322,31 +443,46 @@ def main():
         chk += float(rew_h[0]) + float(done_h[-1])
     barrier()
     staged_s = (time.perf_counter() - t0) * e2e_steps / st_steps     # scaled to e2e_steps for the common reduction below
+    st_step.close()
+    sim_st.close()
 
-    def reduce_max(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
     dev_ms, roll_ms, e2e_s, staged_s = reduce_max(dev_ms), reduce_max(roll_ms), reduce_max(e2e_s), reduce_max(staged_s)
+    contact_rich = None
+    if world == 1 and args.task == "peg-in-hole" and args.arm == "panda":
+        contact_rich = contact_rich_probe(n, local, torch, barrier)
+    for sm in sims:
+        sm.close()
+    if peer is not None:
+        peer.close()
+    del sims, ring
+    torch.cuda.empty_cache()
+    config5 = None
+    if world > 1 and not args.no_config5 and args.task == "peg-in-hole" and args.arm == "panda":
+        config5 = config5_sweep(args, rank, world, local, dev, reduce_max, barrier)
     if rank == 0:
         total_envs = n * world
         value = total_envs * args.steps / (dev_ms * 1e-3)
         kern_s = dev_ms * 1e-3 / args.steps
-        f_run = flops_per_env_step()
-        ach_tf = f_run * n / kern_s / 1e12
+        nj, na = (9, 7) if args.arm == "panda" else (6, 6)
+        f_model = flops_per_env_step(nj, na)                                               # upper bound: 20 IK iterations, 50 sweeps
+        f_exec = flops_per_env_step(nj, na, executed["ik_iters_mean"], executed["pgs_row_iters_mean"], rows_mean)
+        ach_tf = f_exec * n / kern_s / 1e12
         peaks = measured_peaks()
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         ach_gbs = BYTES_PER_ENV_STEP * n / kern_s / 1e9
+        kname = "pih::k_step_ws" if n <= 148 * 128 else ("pih::k_step" if n < 49152 else "pih::k_apply_action + pih::k_step_dyn")
+        cap = NCU_CAPTURES.get((kname, args.arm, args.task, n), {})
         cpu = None
         if not args.no_cpu and world == 1:
             thr = host_threads()
             cn, cst = n, MAX_STEPS                      # one full 200-step episode of the same 4096-env batch (~20 CPU-seconds)
             cpu_oracle_rate(min(cn, 512), 10, thr)
             crate, cdt = cpu_oracle_rate(cn, cst, thr)
+            c1rate, c1dt = cpu_oracle_rate(min(cn, 512), cst, 1)          # BASELINE config 1's shape: one client, one thread
             cpu = {"value": crate, "unit": "env-steps/s", "cores": thr, "kind": "port",
-                   "sample": f"CPU restatement (oracle/, not PyBullet): {cn} envs x {cst} steps of the same workload on {thr} host threads, {cdt:.1f} s wall"}
+                   "sample": f"CPU restatement (oracle/, not PyBullet): {cn} envs x {cst} steps of the same workload on {thr} host threads, {cdt:.1f} s wall",
+                   "single_thread_value": c1rate,
+                   "single_thread_sample": f"{min(cn, 512)} envs x {cst} steps on 1 thread, {c1dt:.1f} s wall (BASELINE config 1: mp_num=1, one core)"}
         line = {
             "metric": "peg-in-hole env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -354,36 +490,41 @@ def main():
             "config": {"workload": f"{args.task} {args.arm}, {n} sub-envs per GPU (BASELINE config 2), dt 1/{round(1 / dt_sim)}, "
                                    f"{MAX_STEPS}-step episodes + auto-reset, U[-1,1]^{adim} actions centred on env origin, offset {list(OFFSET)}",
                        "envs_per_gpu": n, "total_envs": total_envs, "solver_iters": 50, "ik_iters": 20,
-                       "l2": (f"inputs larger than L2: {nb_batches} independent {n}-env batches ({nb_batches * bytes_per_batch / 1e6:.0f} MB of state+actions+outputs) "
-                              "visited round-robin, phases of the 200-step episode spread evenly; K launches inside one CUDA-event pair"
+                       "l2": (f"inputs larger than L2: {nb_batches} independent {n}-env batches ({nb_batches * bytes_per_batch / 1e6:.0f} MB of state+actions+outputs), "
+                              f"batch b pre-rolled to episode phase b*{MAX_STEPS}/{nb_batches} and visited with stride {stride} (coprime), so every window of "
+                              "consecutive steps covers the phases evenly; K launches inside one CUDA-event pair"
                               if args.l2 == "rotate" else "flushed between timed steps (256 MiB memset); per-step CUDA events summed"),
-                       "gather_to_rank0": args.gather or False, "parallelism": f"env-sharded x{world}, no data-path collective"},
+                       "gather_to_rank0": gather if world > 1 else False,
+                       "parallelism": f"env-sharded x{world}, " + ("no data-path collective" if gather == "none" else
+                                                                    ("rows stored into rank 0's learner buffer by the step kernel over NVLink peer memory (no collective)"
+                                                                     if gather == "peer" else "pack + NCCL gather to rank 0 every step"))},
             "e2e": {"value": total_envs * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * adim * 4,
                     "d2h_bytes_per_step": n * (20 + 4 + 1), "steps": e2e_steps,
                     "staged_copy_value": total_envs * e2e_steps / staged_s, "timing": "wall clock per step: pih_step_host on page-locked host buffers = one launch whose SMs read that step's actions from host memory and write obs|reward|done back to host memory over PCIe (zero-copy), stream sync, host reads the result; a fresh i.i.d. host action batch every step; staged_copy_value = the same loop with explicit cudaMemcpyAsync H2D + step + D2H"},
             # one step kernel per env.step; from 49152 envs per GPU on the step is two launches (k_apply_action + k_step_dyn)
             "gpu_launches": args.steps * (2 if n >= 49152 else 1),
             "roofline": {"bound": "fp32", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": (ach_tf / peak_tf) if peak_tf else None, "traffic": NCU_TRAFFIC_BYTES if (args.arm == "panda" and n == ENVS_PER_GPU) else None,
-                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_kstep_ws_ncu_full_v3.csv",
+                         "frac": (ach_tf / peak_tf) if peak_tf else None, "traffic": cap.get("traffic_bytes"),
+                         "traffic_source": cap.get("source"),
                          "peak_source": "in-run FFMA probe (pih_measure_fp32_peak); FP32 pipe is not in MEASURED_PEAKS.json",
-                         "flops_per_env_step": f_run, "flops_per_env_step_bullet_default": FLOPS_BULLET_DEFAULT,
-                         "executed_flops_per_env_step": NCU_EXECUTED_FLOPS_PER_ENV_STEP,
-                         "achieved_executed": NCU_EXECUTED_FLOPS_PER_ENV_STEP * n / kern_s / 1e12,
-                         "frac_executed": (NCU_EXECUTED_FLOPS_PER_ENV_STEP * n / kern_s / 1e12 / peak_tf) if peak_tf else None,
-                         "note": "achieved/frac use SURVEY 8(d)'s algorithmic FLOP model; *_executed use the FP32 thread-instructions ncu counted "
-                                 "(the implementation skips structural zeros and reuses the ABA factorisation, so it executes well under half)",
-                         "kernel": ("pih::k_step_ws" if n <= 148 * 128 else ("pih::k_step" if n < 49152 else "pih::k_apply_action + pih::k_step_dyn")) + f"<{args.arm}, {args.task}>", "kernel_us": kern_s * 1e6,
+                         "flops_per_env_step": f_exec, "executed": executed, "rows_mean": rows_mean,
+                         "flops_per_env_step_model_max": f_model, "achieved_model_max": f_model * n / kern_s / 1e12,
+                         "frac_model_max": (f_model * n / kern_s / 1e12 / peak_tf) if peak_tf else None,
+                         "flops_per_env_step_bullet_default": FLOPS_BULLET_DEFAULT,
+                         "ncu_counted_flops_per_env_step": cap.get("executed_flops_per_env_step"),
+                         "note": "achieved/frac = SURVEY 8(d)'s FLOP formula evaluated with the iteration counts the kernels EXECUTED (in-kernel counters, "
+                                 "sampled over all episode phases right after the timed region) / measured FP32 peak; *_model_max = the same formula at the "
+                                 "configured maxima (20 IK iterations, 50 sweeps over 17 rows); ncu_counted = FP32 thread-instructions of one ncu capture of "
+                                 "this kernel build (null for configs without a capture)",
+                         "kernel": kname + f"<{args.arm}, {args.task}>", "kernel_us": kern_s * 1e6,
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"}},
             "cpu_baseline": cpu,
             "extra": {"rollout_single_launch_value": total_envs * args.steps / (roll_ms * 1e-3),
-                      "wall_s_timed_region": t_wall},
+                      "wall_s_timed_region": t_wall, "contact_rich": contact_rich, "config5": config5},
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
-    for sm in sims:
-        sm.close()
     if world > 1:
         dist.destroy_process_group()
 

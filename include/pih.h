@@ -145,6 +145,12 @@ int pih_grasp_labels(pih_handle* h, int32_t width, int32_t height, float* labels
  * for batches that run the classic kernels a one-thread signalling kernel follows instead). */
 int pih_step_signal(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint32_t* flag_dev,
                     uint32_t flag_value, void* stream);
+/* The learner's rank (the owner of the buffer): pih_step_signal whose kernel FIRST waits until `wait_count` flags have
+ * reached `wait_value` - the consumer's wait for the previous step's rows of every rank, folded into its next launch
+ * instead of a pih_wait_flags kernel of its own (bounded by timeout_ms like pih_wait_flags). */
+int pih_step_signal_wait(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint32_t* flag_dev,
+                         uint32_t flag_value, const uint32_t* wait_flags_dev, int32_t wait_count, uint32_t wait_value, uint32_t timeout_ms,
+                         uint32_t* timed_out_dev, void* stream);
 int pih_peer_alloc(int32_t device, uint64_t bytes, void** ptr_out, uint8_t handle_out[64]);  /* owner: zeroed buffer + its IPC handle */
 int pih_peer_open(int32_t device, const uint8_t handle[64], void** ptr_out);   /* other rank: map it on ITS device (peer memory) */
 int pih_peer_release(void* ptr, int32_t is_owner);

@@ -231,7 +231,22 @@ template <int ARM, int TASK> PIH_D void mailbox_put(float (*mb)[32], int lane, c
   mb[PIH_MB_GRASP_ANG][lane] = S.grasp_ang;
 }
 
-struct StepSignal { unsigned* flag; unsigned value; unsigned* cta_counter; };   // fused "rows delivered" signal (nullable flag)
+// fused "rows delivered" signal (nullable flag) and, for the learner's rank, the consumer-side wait folded into the
+// next launch: before touching anything the CTAs wait until `wait_count` flags have reached `wait_value` (nullable)
+struct StepSignal {
+  unsigned* flag; unsigned value; unsigned* cta_counter;
+  const unsigned* wait_flags; int wait_count; unsigned wait_value; unsigned long long timeout_ns; unsigned* timed_out;
+};
+// bounded spin of one thread on one flag word (steps count up, so >=); records the index of a flag that never came
+PIH_D void wait_flag(const volatile unsigned* flag, unsigned value, unsigned long long timeout_ns, unsigned* timed_out, int idx) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  while ((int)(*flag - value) < 0) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) { atomicExch(timed_out, 1u + (unsigned)idx); break; }
+    __nanosleep(100);
+  }
+}
 
 template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(SimParams P, const float* __restrict__ action, float* __restrict__ obs,
                                                                           float* __restrict__ reward, unsigned char* __restrict__ done,
@@ -242,6 +257,13 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(
   const int e = blockIdx.x * 32 + lane;
   const int ec = e < P.n ? e : P.n - 1;
   pdl_wait();
+  if (sig.wait_flags) {
+    // learner rank: the rows of the previous step of every rank must have landed before this step's rows may follow
+    // (the consumer's wait, folded into its next launch instead of a kernel of its own)
+    if ((int)threadIdx.x < sig.wait_count) wait_flag(sig.wait_flags + threadIdx.x, sig.wait_value, sig.timeout_ns, sig.timed_out, threadIdx.x);
+    __threadfence_system();
+    __syncthreads();
+  }
   // the action row is requested first: with zero-copy host buffers it comes over PCIe, and the state load and the
   // forward kinematics below hide that latency
   float a[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
@@ -422,15 +444,7 @@ __global__ void k_signal_flag(volatile unsigned* flag, unsigned value) {
 // waits until every flag has reached `value` (steps count up, so >=); gives up after `timeout_ns` and records it
 __global__ void k_wait_flags(const volatile unsigned* flags, int count, unsigned value, unsigned long long timeout_ns, unsigned* timed_out) {
   const int i = threadIdx.x;
-  unsigned long long t0, t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  if (i < count) {
-    while ((int)(flags[i] - value) < 0) {
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (t - t0 > timeout_ns) { atomicExch(timed_out, 1u + (unsigned)i); break; }
-      __nanosleep(200);
-    }
-  }
+  if (i < count) wait_flag(flags + i, value, timeout_ns, timed_out, i);
   __threadfence_system();
 }
 
@@ -752,28 +766,44 @@ int pih_reset(pih_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stre
   return PIH_OK;
 }
 
-static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint32_t* flag_dev,
-                     uint32_t flag_value, void* stream);
+static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, StepSignal sig, void* stream);
 
 int pih_step(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, void* stream) {
-  return step_impl(h, action_dev, obs_dev, reward_dev, done_dev, nullptr, 0u, stream);
+  StepSignal sig = {};
+  return step_impl(h, action_dev, obs_dev, reward_dev, done_dev, sig, stream);
 }
 
 int pih_step_signal(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint32_t* flag_dev,
                     uint32_t flag_value, void* stream) {
   if (!flag_dev) return PIH_ERR_INVALID;
-  return step_impl(h, action_dev, obs_dev, reward_dev, done_dev, flag_dev, flag_value, stream);
+  StepSignal sig = {};
+  sig.flag = flag_dev; sig.value = flag_value;
+  return step_impl(h, action_dev, obs_dev, reward_dev, done_dev, sig, stream);
 }
 
-static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint32_t* flag_dev,
-                     uint32_t flag_value, void* stream) {
+int pih_step_signal_wait(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint32_t* flag_dev,
+                         uint32_t flag_value, const uint32_t* wait_flags_dev, int32_t wait_count, uint32_t wait_value, uint32_t timeout_ms,
+                         uint32_t* timed_out_dev, void* stream) {
+  if (!flag_dev || !wait_flags_dev || !timed_out_dev || wait_count <= 0 || wait_count > 64) return PIH_ERR_INVALID;
+  StepSignal sig = {};
+  sig.flag = flag_dev; sig.value = flag_value;
+  sig.wait_flags = wait_flags_dev; sig.wait_count = wait_count; sig.wait_value = wait_value;
+  sig.timeout_ns = (unsigned long long)timeout_ms * 1000000ull; sig.timed_out = timed_out_dev;
+  return step_impl(h, action_dev, obs_dev, reward_dev, done_dev, sig, stream);
+}
+
+static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, StepSignal sig, void* stream) {
   if (!h || !action_dev) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "step() before reset()", cudaSuccess);
   if ((uintptr_t)action_dev & (h->P.arm == PIH_ARM_PANDA ? 15 : 7)) return fail(h, PIH_ERR_INVALID, "action rows must be 16-byte (Box(4)) / 8-byte (Box(6)) aligned", cudaSuccess);
   USE_DEVICE(h);
-  const StepSignal sig = {flag_dev, flag_value, h->d_cta_counter};
+  sig.cta_counter = h->d_cta_counter;
+  uint32_t* const flag_dev = sig.flag;
+  const uint32_t flag_value = sig.value;
   if (h->ws) { LAUNCH_WS(k_step_ws, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev, sig); }
   else {
+    // large batches: the wait and the signal are launches of their own (noise next to a multi-hundred-microsecond step)
+    if (sig.wait_flags) k_wait_flags<<<1, 64, 0, (cudaStream_t)stream>>>(sig.wait_flags, sig.wait_count, sig.wait_value, sig.timeout_ns, sig.timed_out);
     if (h->split && h->P.task != PIH_TASK_SCRIPTED) {
       if (!h->d_qt && cudaMalloc(&h->d_qt, (size_t)h->P.n * PIH_NB_MAX * sizeof(float)) != cudaSuccess)
         return fail(h, PIH_ERR_CUDA, "target scratch allocation", cudaGetLastError());

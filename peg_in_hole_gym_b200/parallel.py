@@ -103,10 +103,8 @@ class PeerLearnerBuffer:
         if counts is None:
             if buf is None and self.world_size > 1:
                 import torch.distributed as dist
-                c = torch.tensor([sim.n], dtype=torch.int64, device=sim.device)
-                cl = [torch.zeros_like(c) for _ in range(self.world_size)]
-                dist.all_gather(cl, c)
-                counts = [int(v.item()) for v in cl]
+                counts = [None] * self.world_size
+                dist.all_gather_object(counts, int(sim.n))
             else:
                 counts = [sim.n] * self.world_size
         self.counts = [int(c) for c in counts]
@@ -188,14 +186,22 @@ class PeerLearnerBuffer:
     def _flag_ptr(self, r):
         return self.base + self.flag_off + 4 * r
 
-    def step(self, action, sim=None):
+    def step(self, action, sim=None, wait_prev=False, timeout_ms=2000):
         """pih_step_signal: this rank's slice of the learner buffer as the outputs; the kernel publishes the step number.
-        ``sim``: another BatchedSim of the same size on this rank (several env batches may feed one learner buffer)."""
+        ``sim``: another BatchedSim of the same size on this rank (several env batches may feed one learner buffer).
+        ``wait_prev`` (owner rank): the kernel first waits until every rank has delivered the PREVIOUS step's rows
+        (pih_step_signal_wait) - the consumer's wait folded into its next launch, no wait kernel of its own; rows of
+        step t are then complete for everything stream-ordered after step t+1 (alternate two buffers to read them
+        while the peers already write step t+1)."""
         from . import _native as N
         sim = self.sim if sim is None else sim
         po, pr, pd, pf = self._my_ptrs
         self.step_no += 1
-        rc = sim._L.pih_step_signal(sim._h, action.data_ptr(), po, pr, pd, pf, self.step_no, sim._stream())
+        if wait_prev and self.step_no > 1:
+            rc = sim._L.pih_step_signal_wait(sim._h, action.data_ptr(), po, pr, pd, pf, self.step_no, self.base + self.flag_off,
+                                            self.world_size, self.step_no - 1, int(timeout_ms), self.timed_out.data_ptr(), sim._stream())
+        else:
+            rc = sim._L.pih_step_signal(sim._h, action.data_ptr(), po, pr, pd, pf, self.step_no, sim._stream())
         if rc:
             N.check(rc, sim._h, "pih_step_signal")
 
@@ -204,7 +210,6 @@ class PeerLearnerBuffer:
         (views of the learner buffer, valid for work enqueued after this call on the same stream)."""
         from . import _native as N
         sim = self.sim
-        self.timed_out.zero_()          # re-armed per wait: a timeout reported by check() belongs to THIS wait
         rc = sim._L.pih_wait_flags(sim._h, self.base + self.flag_off, self.world_size, self.step_no, int(timeout_ms),
                                    self.timed_out.data_ptr(), sim._stream())
         if rc:
@@ -214,8 +219,9 @@ class PeerLearnerBuffer:
         return self._rows
 
     def check(self):
-        """Host-side: raises if the last device-side wait gave up (synchronises the stream).  The rows returned by that
-        wait() are not valid then."""
+        """Host-side: raises if a device-side wait since the previous check() gave up (synchronises the stream); the rows
+        returned by that wait() are not valid then."""
         v = int(self.timed_out.item())
+        self.timed_out.zero_()          # re-armed: the next check() reports only waits that gave up after this one
         if v:
             raise RuntimeError(f"peer gather: rank {v - 1} did not publish step {self.step_no} in time")

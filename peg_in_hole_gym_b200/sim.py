@@ -201,6 +201,22 @@ class BatchedSim:
     def int_word(self, word):
         return self.words(word, 1).contiguous().view(torch.int32)[:, 0]
 
+    def env_offsets_device(self):
+        """World offsets [N, 3] of all envs as a device tensor (BaseEnv._create_env, base_env.py:35-55), computed with
+        torch ops from the closed form - env_offsets() loops over envs on the host, too slow for 10^5+ envs."""
+        c = self.cfg
+        sub = c.sub_num if c.sub_num > 0 else self.n
+        e = (torch.arange(self.n, device=self.device, dtype=torch.int64) + int(c.env_id_base)) % sub
+        ox, oy, oz = float(c.offset[0]), float(c.offset[1]), float(c.offset[2])
+        ef = e.to(torch.float32)
+        if ox == 0.0 or oy == 0.0:
+            return torch.stack([ox * ef, oy * ef, oz * ef], 1)
+        s = 0
+        while s * s < sub:
+            s += 1
+        i, j = (e // s).to(torch.float32), (e % s).to(torch.float32)
+        return torch.stack([ox * i, oy * j, torch.full_like(i, oz)], 1)
+
     def env_offsets(self):
         out = torch.zeros(self.n, 3)
         buf = (C.c_float * 3)()

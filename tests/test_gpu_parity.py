@@ -586,7 +586,8 @@ def test_config5_size_panda_peg_split_kernels():
     a = BatchedSim(n, device=0, **kw); a.reset()
     orc = ol.Oracle(ol.make_config(m, sub_num=n, offset=kw["offset"], seed=55, max_steps=40, auto_reset=1)); orc.reset()
     offs = torch.zeros(n, 4, device="cuda")
-    offs[:, :3] = a.env_offsets().cuda()
+    offs[:, :3] = a.env_offsets_device()
+    assert torch.equal(offs[:300, :3].cpu(), BatchedSim(300, sub_num=n, device=0, **kw).env_offsets())
     g = torch.Generator(device="cuda"); g.manual_seed(5)
     for t in range(50):                                  # crosses one auto-reset
         act = (torch.rand(n, 4, device="cuda", generator=g) * 2 - 1) + offs
