@@ -51,6 +51,9 @@ typedef struct pih_config {
                                2 = fused thread-per-env kernel, 3 = split apply_action + dynamics kernels.  All families compute the
                                same bits (tests/test_gpu_parity.py); the field exists so that every family can be tested at any size */
   int32_t host_path;        /* NEW pih_step_host: 0 = zero-copy when the caller's buffers are page-locked, else staged; 1 = always staged */
+  int32_t peg_model;        /* what the reference's `pipe.urdf` object is simulated as (peg_in_hole.py:240-245): 0 = one rigid end
+                               segment (the round-1 stand-in), 1 = the 25-link chain with 23 continuous joints (panda, tasks 0 and 2).
+                               The state buffer of model 1 has pih_state_words_for(cfg) words per env instead of pih_state_words() */
 } pih_config;
 
 #define PIH_KERNELS_AUTO 0
@@ -62,7 +65,8 @@ typedef struct pih_handle pih_handle;
 
 /* ABI / layout queries */
 int pih_abi_version(void);
-int pih_state_words(void);                 /* 32-bit words of state per env (= 4 * float4 slots) */
+int pih_state_words(void);                 /* 32-bit words of state per env (= 4 * float4 slots), rigid peg model */
+int pih_state_words_for(const pih_config* cfg);   /* the same for any config: 48, or 128 with peg_model = 1 */
 int pih_action_dim(int arm);               /* 4 panda (peg_in_hole.py:12), 6 ur5 (utils.py:70-72) */
 int pih_obs_dim(void);                     /* 5 (peg_in_hole.py:13) */
 

@@ -39,6 +39,10 @@ typedef struct {
   simcfg_d cd;
   envstate_f* sf;
   envstate_d* sd;
+  pipemodel_f pmf;      /* flexible pipe (cfg.peg_model == PIH_PEG_PIPE) */
+  pipemodel_d pmd;
+  pipestate_f* pf;
+  pipestate_d* pd;
   float* off; /* [n][3] */
   uint32_t global_step;
   int* last_nc; /* contacts found by the last step of each env (diagnostics) */
@@ -74,7 +78,11 @@ void* pih_oracle_create(const pih_config* cfg, int use_double) {
   o->cd.auto_reset = cfg->auto_reset; o->cd.action_frame_env = cfg->action_frame_env; o->cd.seed = cfg->seed;
   o->sf = (envstate_f*)calloc(n, sizeof(envstate_f));
   o->sd = (envstate_d*)calloc(n, sizeof(envstate_d));
-  o->off = (float*)calloc(3 * n, sizeof(float));
+  pipemodel_init_f(&o->pmf); pipemodel_init_d(&o->pmd);
+  o->pf = (pipestate_f*)calloc(n, sizeof(pipestate_f));
+  o->pd = (pipestate_d*)calloc(n, sizeof(pipestate_d));
+  for (int i = 0; i < n; ++i) { o->pf[i].bquat[3] = 1.0f; o->pd[i].bquat[3] = 1.0; }
+  o->off = (float*)calloc(3 * (size_t)n, sizeof(float));
   o->last_nc = (int*)calloc(n, sizeof(int));
   for (int i = 0; i < n; ++i) {
     pih_oracle_env_offset(cfg, i, &o->off[3 * i]);
@@ -87,7 +95,7 @@ void* pih_oracle_create(const pih_config* cfg, int use_double) {
 void pih_oracle_destroy(void* h) {
   oracle* o = (oracle*)h;
   if (!o) return;
-  free(o->sf); free(o->sd); free(o->off); free(o->last_nc); free(o);
+  free(o->sf); free(o->sd); free(o->pf); free(o->pd); free(o->off); free(o->last_nc); free(o);
 }
 
 int pih_oracle_reset(void* h, const uint8_t* mask, float* obs) {
@@ -98,7 +106,8 @@ int pih_oracle_reset(void* h, const uint8_t* mask, float* obs) {
     uint32_t gid = (uint32_t)(o->cfg.env_id_base + i);
     if (o->use_double) {
       o->sd[i].episode += 1;
-      reset_env_d(&o->md, &o->cd, &o->sd[i], gid);
+      if (o->cfg.peg_model == PIH_PEG_PIPE) reset_env_pipe_d(&o->md, &o->cd, &o->sd[i], &o->pd[i], gid);
+      else reset_env_d(&o->md, &o->cd, &o->sd[i], gid);
       if (obs) {
         double ob[5], off[3] = {o->off[3 * i], o->off[3 * i + 1], o->off[3 * i + 2]};
         observe_d(&o->md, &o->cd, &o->sd[i], off, ob);
@@ -106,7 +115,8 @@ int pih_oracle_reset(void* h, const uint8_t* mask, float* obs) {
       }
     } else {
       o->sf[i].episode += 1;
-      reset_env_f(&o->mf, &o->cf, &o->sf[i], gid);
+      if (o->cfg.peg_model == PIH_PEG_PIPE) reset_env_pipe_f(&o->mf, &o->cf, &o->sf[i], &o->pf[i], gid);
+      else reset_env_f(&o->mf, &o->cf, &o->sf[i], gid);
       if (obs) observe_f(&o->mf, &o->cf, &o->sf[i], &o->off[3 * i], &obs[5 * i]);
     }
   }
@@ -121,7 +131,8 @@ static int step_one(oracle* o, int i, const float* act, float* obs, float* rewar
     for (int k = 0; k < 6; ++k) a[k] = act[k];
     uint8_t dn = 0;
     if (o->sd[i].flags & PIH_FLAG_DONE) return 0;
-    int nc = step_env_d(&o->md, &o->cd, &o->sd[i], a, off, gid, ob, &rw, &dn);
+    int nc = (o->cfg.peg_model == PIH_PEG_PIPE) ? step_env_pipe_d(&o->md, &o->pmd, &o->cd, &o->sd[i], &o->pd[i], a, off, gid, ob, &rw, &dn)
+                                               : step_env_d(&o->md, &o->cd, &o->sd[i], a, off, gid, ob, &rw, &dn);
     o->last_nc[i] = nc;
     if (obs) for (int k = 0; k < 5; ++k) obs[k] = (float)ob[k];
     if (reward) *reward = (float)rw;
@@ -131,7 +142,8 @@ static int step_one(oracle* o, int i, const float* act, float* obs, float* rewar
     float ob[5], rw = 0;
     uint8_t dn = 0;
     if (o->sf[i].flags & PIH_FLAG_DONE) return 0;
-    int nc = step_env_f(&o->mf, &o->cf, &o->sf[i], act, &o->off[3 * i], gid, ob, &rw, &dn);
+    int nc = (o->cfg.peg_model == PIH_PEG_PIPE) ? step_env_pipe_f(&o->mf, &o->pmf, &o->cf, &o->sf[i], &o->pf[i], act, &o->off[3 * i], gid, ob, &rw, &dn)
+                                               : step_env_f(&o->mf, &o->cf, &o->sf[i], act, &o->off[3 * i], gid, ob, &rw, &dn);
     o->last_nc[i] = nc;
     if (obs) for (int k = 0; k < 5; ++k) obs[k] = ob[k];
     if (reward) *reward = rw;
@@ -199,10 +211,28 @@ void pih_oracle_last_contacts(void* h, int* out) {
 
 /* state exchange in the device layout: words[slot][env][4] (float4 SoA, pih_constants.h) */
 #define WIDX(w, i, n) ((size_t)((w) >> 2) * (size_t)(n) * 4 + (size_t)(i) * 4 + ((w) & 3))
+int pih_oracle_state_words(const pih_config* cfg) { return cfg->peg_model == PIH_PEG_PIPE ? 4 * PIH_PIPE_STATE_F4 : PIH_STATE_WORDS; }
+
 int pih_oracle_get_state(void* h, float* words) {
   oracle* o = (oracle*)h;
   int n = o->cfg.num_envs;
-  memset(words, 0, sizeof(float) * PIH_STATE_WORDS * (size_t)n);
+  memset(words, 0, sizeof(float) * (size_t)pih_oracle_state_words(&o->cfg) * (size_t)n);
+  if (o->cfg.peg_model == PIH_PEG_PIPE)
+    for (int i = 0; i < n; ++i) {
+      const int D = o->use_double;
+      for (int k = 0; k < 3; ++k) {
+        words[WIDX(PIH_PS_POS + k, i, n)] = D ? (float)o->pd[i].bpos[k] : o->pf[i].bpos[k];
+        words[WIDX(PIH_PS_VEL + k, i, n)] = D ? (float)o->pd[i].bvel[k] : o->pf[i].bvel[k];
+        words[WIDX(PIH_PS_ANG + k, i, n)] = D ? (float)o->pd[i].bang[k] : o->pf[i].bang[k];
+      }
+      for (int k = 0; k < 4; ++k) words[WIDX(PIH_PS_QUAT + k, i, n)] = D ? (float)o->pd[i].bquat[k] : o->pf[i].bquat[k];
+      int32_t gi = D ? o->pd[i].grasp_idx : o->pf[i].grasp_idx;
+      memcpy(&words[WIDX(PIH_PS_GRASP, i, n)], &gi, 4);
+      for (int b = 1; b < PIH_PIPE_NBODY; ++b) {
+        words[WIDX(PIH_PS_QJ + b - 1, i, n)] = D ? (float)o->pd[i].qj[b] : o->pf[i].qj[b];
+        words[WIDX(PIH_PS_QDJ + b - 1, i, n)] = D ? (float)o->pd[i].qdj[b] : o->pf[i].qdj[b];
+      }
+    }
   for (int i = 0; i < n; ++i) {
     int32_t ints[3];
     for (int k = 0; k < PIH_NB_MAX; ++k) {
@@ -236,6 +266,22 @@ int pih_oracle_get_state(void* h, float* words) {
 int pih_oracle_set_state(void* h, const float* words) {
   oracle* o = (oracle*)h;
   int n = o->cfg.num_envs;
+  if (o->cfg.peg_model == PIH_PEG_PIPE)
+    for (int i = 0; i < n; ++i) {
+      for (int k = 0; k < 3; ++k) {
+        o->pf[i].bpos[k] = words[WIDX(PIH_PS_POS + k, i, n)]; o->pd[i].bpos[k] = o->pf[i].bpos[k];
+        o->pf[i].bvel[k] = words[WIDX(PIH_PS_VEL + k, i, n)]; o->pd[i].bvel[k] = o->pf[i].bvel[k];
+        o->pf[i].bang[k] = words[WIDX(PIH_PS_ANG + k, i, n)]; o->pd[i].bang[k] = o->pf[i].bang[k];
+      }
+      for (int k = 0; k < 4; ++k) { o->pf[i].bquat[k] = words[WIDX(PIH_PS_QUAT + k, i, n)]; o->pd[i].bquat[k] = o->pf[i].bquat[k]; }
+      int32_t gi;
+      memcpy(&gi, &words[WIDX(PIH_PS_GRASP, i, n)], 4);
+      o->pf[i].grasp_idx = o->pd[i].grasp_idx = gi;
+      for (int b = 1; b < PIH_PIPE_NBODY; ++b) {
+        o->pf[i].qj[b] = words[WIDX(PIH_PS_QJ + b - 1, i, n)]; o->pd[i].qj[b] = o->pf[i].qj[b];
+        o->pf[i].qdj[b] = words[WIDX(PIH_PS_QDJ + b - 1, i, n)]; o->pd[i].qdj[b] = o->pf[i].qdj[b];
+      }
+    }
   for (int i = 0; i < n; ++i) {
     int32_t ints[3];
     memcpy(&ints[0], &words[WIDX(PIH_S_STEP, i, n)], 4);
@@ -401,4 +447,33 @@ int pih_oracle_render(void* h, int W, int H, int lo, int hi, float* out) {
     }
   }
   return 0;
+}
+
+/* flexible-pipe dynamics hook (double): unconstrained velocities after dt and the unit-impulse responses col[i][j]
+ * (tests pin them against an independent numpy model: mass matrix from body Jacobians + recursive Newton-Euler bias) */
+void pih_oracle_pipe_dyn(const double* bquat, const double* bvel, const double* bang, const double* qj, const double* qdj, double dt, double g,
+                         double* vstar, double* col) {
+  pipemodel_d PM; pipemodel_init_d(&PM);
+  pipestate_d PS; memset(&PS, 0, sizeof(PS));
+  for (int k = 0; k < 4; ++k) PS.bquat[k] = bquat[k];
+  for (int k = 0; k < 3; ++k) { PS.bvel[k] = bvel[k]; PS.bang[k] = bang[k]; }
+  for (int b = 1; b < PIH_PIPE_NBODY; ++b) { PS.qj[b] = qj[b - 1]; PS.qdj[b] = qdj[b - 1]; }
+  pipefk_d K; pipe_fk_d(&PS, &K);
+  pipedyn_d D; pipe_dynamics_d(&PM, &PS, &K, dt, g, &D);
+  for (int i = 0; i < PIH_PIPE_NDOF; ++i) {
+    vstar[i] = D.vstar[i];
+    for (int j = 0; j < PIH_PIPE_NDOF; ++j) col[i * PIH_PIPE_NDOF + j] = D.col[i][j];
+  }
+}
+/* world poses of the 24 pipe bodies for a given state: pos[24][3], rot[24][9] */
+void pih_oracle_pipe_fk(const double* bpos, const double* bquat, const double* qj, double* pos, double* rot) {
+  pipestate_d PS; memset(&PS, 0, sizeof(PS));
+  for (int k = 0; k < 4; ++k) PS.bquat[k] = bquat[k];
+  for (int k = 0; k < 3; ++k) PS.bpos[k] = bpos[k];
+  for (int b = 1; b < PIH_PIPE_NBODY; ++b) PS.qj[b] = qj[b - 1];
+  pipefk_d K; pipe_fk_d(&PS, &K);
+  for (int b = 0; b < PIH_PIPE_NBODY; ++b) {
+    pos[3 * b] = K.pw[b].x; pos[3 * b + 1] = K.pw[b].y; pos[3 * b + 2] = K.pw[b].z;
+    for (int i = 0; i < 9; ++i) rot[9 * b + i] = K.Rw[b].m[i / 3][i % 3];
+  }
 }

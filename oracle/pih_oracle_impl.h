@@ -1126,20 +1126,16 @@ static void FN(render_pixel)(const model* M, const simcfg* C, const scene* SC, i
   }
 }
 
-/* returns contact count; outputs written only if the env was stepped (done envs are frozen: base_env.py:61-71) */
-static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real* action, const real off[3], uint32_t gid,
-                        real* obs, real* reward, uint8_t* done) {
-  if (S->flags & PIH_FLAG_DONE) return 0;
+/* apply_action: panda_execute / ur_execute (envs/utils.py:60-82), or the scripted state machine of the shipped task
+ * (peg_in_hole.py:39-212): joint position targets, gains and force caps of this step.  F = FK of S->q. */
+static void FN(apply_action)(const model* M, const simcfg* C, envstate* S, const fkres* Fp, const real* action, const real off[3],
+                             real* qstar, real* kpc, real* mfc, int* fsm_done_out) {
   const int nb = M->nb;
-  const real dt = C->dt;
-  /* ---- apply_action: panda_execute / ur_execute (envs/utils.py:60-82) ---- */
-  fkres F;
-  FN(fk)(M, S->q, nb, &F);
+  const fkres F = *Fp;
   v3 pee; m3 Ree;
   FN(ee_pose)(M, &F, &pee, &Ree);
   v3 tgt;
   real tq[4];
-  real qstar[NBM], kpc[NBM], mfc[NBM];
   int fsm_done = 0;
   for (int j = 0; j < nb; ++j) { kpc[j] = M->kp[j]; mfc[j] = M->maxf[j]; }
   if (C->task == PIH_TASK_SCRIPTED) {
@@ -1212,6 +1208,20 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
     FN(ik_dls)(M, C, &F, S->q, tgt, tq, qstar);
     for (int j = M->narm; j < nb; ++j) qstar[j] = action[3];         /* fingers = action[3]: utils.py:66,68 */
   }
+  *fsm_done_out = fsm_done;
+}
+
+/* returns contact count; outputs written only if the env was stepped (done envs are frozen: base_env.py:61-71) */
+static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real* action, const real off[3], uint32_t gid,
+                        real* obs, real* reward, uint8_t* done) {
+  if (S->flags & PIH_FLAG_DONE) return 0;
+  const int nb = M->nb;
+  const real dt = C->dt;
+  fkres F;
+  FN(fk)(M, S->q, nb, &F);
+  real qstar[NBM], kpc[NBM], mfc[NBM];
+  int fsm_done = 0;
+  FN(apply_action)(M, C, S, &F, action, off, qstar, kpc, mfc, &fsm_done);
   /* ---- stepSimulation: unconstrained accelerations ---- */
   real tau[NBM];
   for (int i = 0; i < nb; ++i) tau[i] = -(M->damp[i] * S->qd[i]);
@@ -1492,6 +1502,8 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
   }
   return CS.n;
 }
+
+#include "pih_pipe_impl.h"
 
 #undef real
 #undef v3

@@ -23,7 +23,7 @@ class PihConfig(C.Structure):
                 ("sub_num", C.c_int32), ("env_id_base", C.c_int32), ("offset", C.c_float * 3), ("dt", C.c_float), ("solver_residual", C.c_float),
                 ("solver_iters", C.c_int32), ("ik_iters", C.c_int32), ("max_steps", C.c_int32),
                 ("auto_reset", C.c_int32), ("action_frame_env", C.c_int32), ("device", C.c_int32),
-                ("seed", C.c_uint64), ("kernel_family", C.c_int32), ("host_path", C.c_int32)]
+                ("seed", C.c_uint64), ("kernel_family", C.c_int32), ("host_path", C.c_int32), ("peg_model", C.c_int32)]
 
 
 class NativeLibraryMissing(ImportError):
@@ -46,6 +46,8 @@ def lib():
     vp, i32 = C.c_void_p, C.c_int32
     L.pih_abi_version.restype = C.c_int
     L.pih_state_words.restype = C.c_int
+    L.pih_state_words_for.restype = C.c_int
+    L.pih_state_words_for.argtypes = [C.POINTER(PihConfig)]
     L.pih_action_dim.argtypes = [C.c_int]
     L.pih_obs_dim.restype = C.c_int
     L.pih_create.argtypes = [C.POINTER(PihConfig), vp, C.POINTER(vp)]
@@ -85,18 +87,20 @@ def lib():
     return L
 
 
-EXPORTS = ["pih_abi_version", "pih_state_words", "pih_action_dim", "pih_obs_dim", "pih_create", "pih_destroy",
+EXPORTS = ["pih_abi_version", "pih_state_words", "pih_state_words_for", "pih_action_dim", "pih_obs_dim", "pih_create", "pih_destroy",
            "pih_last_error", "pih_env_offset", "pih_reset", "pih_step", "pih_step_host", "pih_rollout",
            "pih_ik_targets", "pih_ee_pose", "pih_render", "pih_grasp_labels", "pih_step_signal", "pih_peer_alloc", "pih_peer_open", "pih_peer_release",
            "pih_enable_peer", "pih_signal_flag",
            "pih_wait_flags", "pih_measure_fp32_peak", "pih_host_bind", "pih_host_unbind", "pih_set_stats", "pih_step_signal_wait"]
 KERNEL_FAMILIES = {"auto": 0, "ws": 1, "fused": 2, "split": 3}
+PEG_MODELS = {"rigid": 0, "pipe": 1}      # pih_config.peg_model: one rigid segment / the reference's 25-link pipe.urdf chain
 
 
 def make_config(num_envs, task="peg-in-hole", arm="panda", fly_object="banana", sub_num=None, env_id_base=0,
                 offset=(0.0, 0.0, 0.0), dt=1.0 / 240.0, solver_residual=1e-7, solver_iters=50, ik_iters=20, max_steps=0, auto_reset=False,
-                action_frame_env=False, device=0, seed=0, kernel_family="auto", host_path=0):
+                action_frame_env=False, device=0, seed=0, kernel_family="auto", host_path=0, peg_model="rigid"):
     c = PihConfig()
+    c.peg_model = PEG_MODELS[peg_model] if isinstance(peg_model, str) else int(peg_model)
     c.kernel_family = KERNEL_FAMILIES[kernel_family] if isinstance(kernel_family, str) else int(kernel_family)
     c.host_path = int(host_path)
     c.task = TASK_IDS[task] if isinstance(task, str) else int(task)

@@ -82,6 +82,48 @@
 #define PIH_MU_DEFAULT 0.5              /* Bullet default lateral friction [3P] */
 #define PIH_MU_FINGER 1.0               /* panda finger lateral_friction [3P] */
 
+/* flexible pipe (assets/urdf/pipe.urdf, globalScaling 0.01, peg_in_hole.py:240-245): 25 links pipe_link0..24, each a
+ * cylinder r = 1, y in [0, 6] mesh units in its link frame (collision origin (0,3,0), pipe.urdf:29-35); link1 hangs on
+ * link0 by a FIXED joint at (0,3,0) (pipe.urdf:39-43), links 2..24 by continuous joints at (0,5.5,0) of their parent with
+ * axes alternating z (even link numbers) / x (odd) (pipe.urdf:76-83,109-116,...).  Bodies of the multibody: 0 = link0 +
+ * link1 (floating base), b = 1..23 = link b+1.  Masses pipe.urdf:16,54,87,...; link1's inertial origin (0,1.5,0)
+ * (pipe.urdf:53), every other link's at its frame origin; inertia = box of the collision AABB + 1 mm margin about that
+ * origin (Bullet default URDF loading [3P]); lateral friction 100 on links 0, 1, 23, 24 (pipe.urdf:10,48,765,802). */
+#define PIH_PEG_RIGID 0         /* pih_config.peg_model: one rigid end segment (round-1 stand-in) */
+#define PIH_PEG_PIPE 1          /* pih_config.peg_model: the 25-link chain */
+#define PIH_PIPE_NSEG 25
+#define PIH_PIPE_NBODY 24
+#define PIH_PIPE_NJ 23
+#define PIH_PIPE_NDOF 29        /* 6 base + 23 joints */
+#define PIH_PIPE_R 0.01
+#define PIH_PIPE_HL 0.03
+#define PIH_PIPE_PITCH 0.055
+#define PIH_PIPE_LINK1_Y 0.03
+#define PIH_PIPE_LINK_MASS 0.0111
+#define PIH_PIPE_LINK0_MASS 0.00111
+#define PIH_PIPE_LINK1_COM_Y 0.015
+#define PIH_PIPE_MU_END 100.0
+#define PIH_PIPE_MOTOR_IMPULSE 1.0   /* default velocity motor of every movable joint: target 0, max impulse 1 per step [3P] */
+#define PIH_PIPE_BEND_MAX 1.0471975511965976   /* random.uniform(0, pi/3), peg_in_hole.py:245 */
+#define PIH_PIPE_SEG_MAXC 2     /* contact points kept per segment per step (deepest first) */
+#define PIH_PIPE_ARM_MAXC 4     /* arm-sphere <-> table contacts kept per step (deepest first) */
+#define PIH_PIPE_SEG_TOTAL 32   /* pipe contact points solved per step: every segment's deeper point first (segment order), then the
+                                   second points, until 32 (a pipe lying flat keeps 25 + 7) */
+#define PIH_PIPE_MAXC (PIH_PIPE_SEG_TOTAL + PIH_PIPE_ARM_MAXC)
+#define PIH_PIPE_ARMROWS 16     /* of those, contact points that involve the arm (finger / arm sphere <-> segment, arm <-> table):
+                                   later ones are dropped */
+/* pipe task state: float4 slots 16..31 of a PIH_PIPE_STATE_F4-slot buffer (slots 0..11 as above, 12..15 reserved) */
+#define PIH_PIPE_STATE_F4 32
+#define PIH_PS_BASE 64          /* first word of the pipe block */
+#define PIH_PS_POS (PIH_PS_BASE + 0)    /* 3: base (pipe_link0 frame) position, env frame */
+#define PIH_PS_QUAT (PIH_PS_BASE + 3)   /* 4: x,y,z,w */
+#define PIH_PS_VEL (PIH_PS_BASE + 7)    /* 3: linear velocity of the base origin, env frame */
+#define PIH_PS_ANG (PIH_PS_BASE + 10)   /* 3: angular velocity, env frame */
+#define PIH_PS_GRASP (PIH_PS_BASE + 13) /* int bits: grasp_joint_idx, 0 or 23 (peg_in_hole.py:266) */
+#define PIH_PS_QJ (PIH_PS_BASE + 16)    /* 23 joint angles */
+#define PIH_PS_QDJ (PIH_PS_BASE + 40)   /* 23 joint rates */
+#define PIH_PAIR_PIPE_SELF 64    /* (reserved) */
+
 /* random-fly free bodies (assets/urdf/banana.urdf:5-15; Amicelli_800_tex.urdf:5-15): mass 1, mu 0;
  * collision = AABB box of the convex pieces */
 #define PIH_FLY_MASS 1.0

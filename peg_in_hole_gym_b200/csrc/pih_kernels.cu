@@ -9,6 +9,7 @@
 
 #include "../../include/pih.h"
 #include "pih_render.cuh"
+#include "pih_pipe_host.h"
 
 namespace pih {
 
@@ -44,20 +45,6 @@ template <int ARM> PIH_D void frozen_outputs(const EnvState& S, v3 off, float (&
   observe<ARM>(S, off, o);
   r = (S.flags & PIH_FLAG_SUCCESS) ? 1.0f : 0.0f;
   d = 1;
-}
-
-// one env's action row: a single 128-bit load for Box(4), three 64-bit loads for Box(6) (rows are 16 B / 24 B apart)
-template <int A> PIH_D void load_action(const float* __restrict__ action, int e, float (&a)[6]) {
-  if (A == 4) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(action) + e);
-    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; a[4] = 0.0f; a[5] = 0.0f;
-  } else {
-#pragma unroll
-    for (int k = 0; k < A / 2; ++k) {
-      float2 v = __ldg(reinterpret_cast<const float2*>(action) + (size_t)(A / 2) * e + k);
-      a[2 * k] = v.x; a[2 * k + 1] = v.y;
-    }
-  }
 }
 
 template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOCKS) k_step(SimParams P, const float* __restrict__ action, float* __restrict__ obs,
@@ -448,10 +435,12 @@ __global__ void k_wait_flags(const volatile unsigned* flags, int count, unsigned
   __threadfence_system();
 }
 
-__global__ void k_init_state(float4* state, int n) {
+__global__ void k_init_state(float4* state, int n, int slots) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
-  for (int s = 0; s < PIH_STATE_F4; ++s) state[(size_t)s * n + e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  for (int s = 0; s < slots; ++s) state[(size_t)s * n + e] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (slots > (PIH_PS_QUAT + 3) / 4)   // flexible pipe: identity base orientation
+    reinterpret_cast<float*>(&state[(size_t)((PIH_PS_QUAT + 3) >> 2) * n + e])[(PIH_PS_QUAT + 3) & 3] = 1.0f;
   // episode = -1 (no reset yet), identity quaternion
   reinterpret_cast<float*>(&state[(size_t)(PIH_S_EPISODE >> 2) * n + e])[PIH_S_EPISODE & 3] = __int_as_float(-1);
   reinterpret_cast<float*>(&state[(size_t)((PIH_S_PQUAT + 3) >> 2) * n + e])[(PIH_S_PQUAT + 3) & 3] = 1.0f;
@@ -497,6 +486,8 @@ struct pih_handle {
   size_t bind_bytes[PIH_ALIAS_SLOTS];
   char* bind_dev[PIH_ALIAS_SLOTS];
   int n_bind, no_zero_copy;
+  int pipe;                  // peg_model == PIH_PEG_PIPE: the flexible-pipe kernels (pih_pipe.cu)
+  float* d_pipe_scratch;     // per-env block between k_pipe_arm and k_pipe_step
   unsigned* d_cta_counter;   // fused step signal: CTAs that have delivered their rows (re-armed by the last one)
 };
 
@@ -522,50 +513,7 @@ struct DeviceGuard {
   DeviceGuard guard_((h)->cfg.device);                                                 \
   if (!guard_.ok) return fail((h), PIH_ERR_CUDA, "cudaSetDevice", cudaGetLastError())
 
-#define FILL_ARM(T, P)                                                                          \
-  do {                                                                                          \
-    (T).nb = PIH_##P##_NB; (T).narm = PIH_##P##_NARM; (T).ee_body = PIH_##P##_EE_BODY;            \
-    (T).nsph = PIH_##P##_NSPH; (T).nbox = PIH_##P##_NBOX;                                       \
-    for (int i = 0; i < PIH_##P##_NB; ++i) {                                                    \
-      (T).parent[i] = PIH_##P##_PARENT[i]; (T).jtype[i] = PIH_##P##_JTYPE[i];                    \
-      unsigned a = 1u << i;                                                                     \
-      for (int p = PIH_##P##_PARENT[i]; p >= 0; p = PIH_##P##_PARENT[p]) a |= 1u << p;           \
-      (T).anc[i] = a;                                                                           \
-      for (int r = 0; r < 3; ++r) {                                                             \
-        for (int c = 0; c < 3; ++c) {                                                           \
-          (T).R0[i][r][c] = (float)PIH_##P##_R0[i][3 * r + c];                                   \
-          (T).Irot[i][r][c] = (float)PIH_##P##_IROT[i][3 * r + c];                               \
-        }                                                                                       \
-        (T).t0[i][r] = (float)PIH_##P##_T0[i][r]; (T).h[i][r] = (float)PIH_##P##_H[i][r];         \
-      }                                                                                         \
-      (T).mass[i] = (float)PIH_##P##_MASS[i]; (T).lo[i] = (float)PIH_##P##_LO[i]; (T).hi[i] = (float)PIH_##P##_HI[i]; \
-      (T).damp[i] = (float)PIH_##P##_DAMP[i]; (T).maxf[i] = (float)PIH_##P##_MAXF[i];            \
-      (T).kp[i] = (float)PIH_##P##_KP[i]; (T).rest[i] = (float)PIH_##P##_REST[i];                \
-    }                                                                                           \
-    for (int r = 0; r < 3; ++r) {                                                               \
-      for (int c = 0; c < 3; ++c) (T).ee_R[r][c] = (float)PIH_##P##_EE_R[3 * r + c];             \
-      (T).ee_t[r] = (float)PIH_##P##_EE_T[r];                                                   \
-    }                                                                                           \
-    for (int s = 0; s < PIH_MAX_SPH; ++s) {                                                     \
-      (T).sph_body[s] = PIH_##P##_SPH_BODY[s]; (T).sph_r[s] = (float)PIH_##P##_SPH_R[s];         \
-      for (int r = 0; r < 3; ++r) (T).sph_c[s][r] = (float)PIH_##P##_SPH_C[s][r];                \
-    }                                                                                           \
-    for (int s = 0; s < PIH_MAX_BOX; ++s) {                                                     \
-      (T).box_body[s] = PIH_##P##_BOX_BODY[s];                                                  \
-      for (int r = 0; r < 3; ++r) {                                                             \
-        (T).box_c[s][r] = (float)PIH_##P##_BOX_C[s][r]; (T).box_h[s][r] = (float)PIH_##P##_BOX_H[s][r]; \
-        for (int c = 0; c < 3; ++c) (T).box_R[s][r][c] = (float)PIH_##P##_BOX_R[s][3 * r + c];   \
-      }                                                                                         \
-    }                                                                                           \
-  } while (0)
-
-static cudaError_t upload_tables() {
-  static ArmTables host[2];
-  memset(host, 0, sizeof(host));
-  FILL_ARM(host[PIH_ARM_PANDA], PANDA);
-  FILL_ARM(host[PIH_ARM_UR5], UR5);
-  return cudaMemcpyToSymbol(c_arm, host, sizeof(host));
-}
+#include "pih_tables_host.h"
 
 // launch of the small-batch kernels with programmatic stream serialisation (see pdl_wait)
 template <typename... KArgs, typename... Args>
@@ -583,6 +531,7 @@ extern "C" {
 
 int pih_abi_version(void) { return PIH_ABI_VERSION; }
 int pih_state_words(void) { return PIH_STATE_WORDS; }
+int pih_state_words_for(const pih_config* cfg) { return (cfg && cfg->peg_model == PIH_PEG_PIPE) ? 4 * PIH_PIPE_STATE_F4 : PIH_STATE_WORDS; }
 int pih_action_dim(int arm) { return arm == PIH_ARM_PANDA ? 4 : (arm == PIH_ARM_UR5 ? 6 : PIH_ERR_INVALID); }
 int pih_obs_dim(void) { return 5; }
 
@@ -610,6 +559,9 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   // the ur5 variant exists for the peg-in-hole task (utils.py:40-48,70-82); random-fly and the scripted episode are
   // panda tasks (README.md:38, peg_in_hole.py:233), and their ur5 kernels are not instantiated
   if (cfg->arm == PIH_ARM_UR5 && cfg->task != PIH_TASK_PEG_IN_HOLE) return PIH_ERR_INVALID;
+  if (cfg->peg_model != PIH_PEG_RIGID && cfg->peg_model != PIH_PEG_PIPE) return PIH_ERR_INVALID;
+  // the pipe is the panda tasks' object (peg_in_hole.py:233-245): 'peg-in-hole' and the scripted episode
+  if (cfg->peg_model == PIH_PEG_PIPE && (cfg->arm != PIH_ARM_PANDA || cfg->task == PIH_TASK_RANDOM_FLY)) return PIH_ERR_INVALID;
   if (cfg->kernel_family < 0 || cfg->kernel_family > 3 || cfg->host_path < 0 || cfg->host_path > 1) return PIH_ERR_INVALID;
   if (!(cfg->dt > 0.0f) || cfg->solver_iters < 0 || cfg->ik_iters < 0 || !(cfg->solver_residual >= 0.0f)) return PIH_ERR_INVALID;
   // reference assert: task_num == 1 or offset != [0,0,0] (envs/base_env.py:17)
@@ -669,8 +621,11 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   else if (cfg->kernel_family == PIH_KERNELS_FUSED) { h->ws = 0; h->split = 0; }
   else if (cfg->kernel_family == PIH_KERNELS_SPLIT) { h->ws = 0; h->split = 1; }
   h->no_zero_copy = cfg->host_path == 1;
-  k_init_state<<<(P.n + 127) / 128, 128>>>(P.state, P.n);
+  h->pipe = cfg->peg_model == PIH_PEG_PIPE;
+  k_init_state<<<(P.n + 127) / 128, 128>>>(P.state, P.n, h->pipe ? PIH_PIPE_STATE_F4 : PIH_STATE_F4);
   cudaError_t ce = cudaGetLastError();
+  if (ce == cudaSuccess && h->pipe) ce = pih_pipe_upload_tables();
+  if (ce == cudaSuccess && h->pipe) ce = cudaMalloc(&h->d_pipe_scratch, pih_pipe_scratch_bytes(P.n));
   if (ce == cudaSuccess) ce = cudaMalloc(&h->d_cta_counter, sizeof(unsigned));
   if (ce == cudaSuccess) ce = cudaMemset(h->d_cta_counter, 0, sizeof(unsigned));
   if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
@@ -682,6 +637,7 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
 void pih_destroy(pih_handle* h) {
   if (!h) return;
   if (h->d_cta_counter) cudaFree(h->d_cta_counter);
+  if (h->d_pipe_scratch) cudaFree(h->d_pipe_scratch);
   if (h->d_qt) cudaFree(h->d_qt);
   if (h->h_action) cudaFreeHost(h->h_action);
   if (h->h_obs) cudaFreeHost(h->h_obs);     // one pinned block: obs | reward | done
@@ -759,7 +715,8 @@ const char* pih_last_error(const pih_handle* h) { return h ? h->err : "null hand
 int pih_reset(pih_handle* h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (!h) return PIH_ERR_INVALID;
   USE_DEVICE(h);
-  LAUNCH(k_reset, h, stream, h->P, mask_dev, obs_dev);
+  if (h->pipe) pih_pipe_launch_reset(h->P, mask_dev, obs_dev, (cudaStream_t)stream);
+  else LAUNCH(k_reset, h, stream, h->P, mask_dev, obs_dev);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_reset launch", ce);
   h->was_reset = 1;
@@ -800,7 +757,11 @@ static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, flo
   sig.cta_counter = h->d_cta_counter;
   uint32_t* const flag_dev = sig.flag;
   const uint32_t flag_value = sig.value;
-  if (h->ws) { LAUNCH_WS(k_step_ws, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev, sig); }
+  if (h->pipe) {
+    if (sig.wait_flags) k_wait_flags<<<1, 64, 0, (cudaStream_t)stream>>>(sig.wait_flags, sig.wait_count, sig.wait_value, sig.timeout_ns, sig.timed_out);
+    pih_pipe_launch_step(h->P, action_dev, h->d_pipe_scratch, obs_dev, reward_dev, done_dev, nullptr, (cudaStream_t)stream);
+    if (flag_dev) k_signal_flag<<<1, 1, 0, (cudaStream_t)stream>>>(flag_dev, flag_value);
+  } else if (h->ws) { LAUNCH_WS(k_step_ws, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev, sig); }
   else {
     // large batches: the wait and the signal are launches of their own (noise next to a multi-hundred-microsecond step)
     if (sig.wait_flags) k_wait_flags<<<1, 64, 0, (cudaStream_t)stream>>>(sig.wait_flags, sig.wait_count, sig.wait_value, sig.timeout_ns, sig.timed_out);
@@ -945,6 +906,16 @@ int pih_rollout(pih_handle* h, int32_t steps, float* obs_dev, float* reward_dev,
   if (!h || steps < 0) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "rollout() before reset()", cudaSuccess);
   USE_DEVICE(h);
+  if (h->pipe) {
+    // the pipe step is two launches (thread-per-env arm half, warp-per-env chain): `steps` of them, Philox actions in-kernel
+    for (int t = 0; t < steps; ++t) {
+      pih_pipe_launch_step(h->P, nullptr, h->d_pipe_scratch, obs_dev, reward_dev, done_dev, counters_dev, (cudaStream_t)stream);
+      h->P.global_step += 1;
+    }
+    cudaError_t cep = cudaGetLastError();
+    if (cep != cudaSuccess) return fail(h, PIH_ERR_CUDA, "pipe rollout launch", cep);
+    return PIH_OK;
+  }
   if (h->ws) { LAUNCH_WS(k_rollout_ws, h, stream, h->P, (int)steps, obs_dev, reward_dev, done_dev, counters_dev); }
   else if (h->split && h->P.task != PIH_TASK_SCRIPTED) {
     // large batches: the two-kernel step (see k_apply_action), `steps` times; at these sizes a launch is noise

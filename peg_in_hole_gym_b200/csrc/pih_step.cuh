@@ -38,7 +38,7 @@ struct ContactSet {
 
 // keep the PIH_MAXC deepest candidates; ties keep the earlier candidate.  The margin test is inlined at every
 // candidate site; the (rare) insertion is one out-of-line copy so that it does not bloat the instruction stream.
-__device__ __noinline__ void contact_insert(ContactSet& S, const Contact& c) {
+static __device__ __noinline__ void contact_insert(ContactSet& S, const Contact& c) {
   if (S.n < PIH_MAXC) { S.c[S.n++] = c; return; }
   int w = 0;
   for (int i = 1; i < PIH_MAXC; ++i)
@@ -489,6 +489,20 @@ template <int ARM, int TASK> __device__ __noinline__ bool step_env(const SimPara
   stat_add(P, PIH_STAT_IK_ITERS, (unsigned)ik_n);
   step_back<ARM, TASK>(P, S, F, qstar, kpc, mfc, fsm_done, true, off, gid, obs, reward, done);
   return true;
+}
+
+// one env's action row: a single 128-bit load for Box(4), three 64-bit loads for Box(6) (rows are 16 B / 24 B apart)
+template <int A> PIH_D void load_action(const float* __restrict__ action, int e, float (&a)[6]) {
+  if (A == 4) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(action) + e);
+    a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; a[4] = 0.0f; a[5] = 0.0f;
+  } else {
+#pragma unroll
+    for (int k = 0; k < A / 2; ++k) {
+      float2 v = __ldg(reinterpret_cast<const float2*>(action) + (size_t)(A / 2) * e + k);
+      a[2 * k] = v.x; a[2 * k + 1] = v.y;
+    }
+  }
 }
 
 }  // namespace pih

@@ -52,23 +52,24 @@ class HostStepper:
 
 class BatchedSim:
     """num_envs sub-environments resident on one GPU.  State lives in a torch-owned float4-SoA tensor
-    ``state[12, N, 4]`` (layout: csrc/pih_constants.h); outputs in ``obs[N,5]``, ``reward[N]``, ``done[N]``."""
+    ``state[12, N, 4]`` (``[32, N, 4]`` with ``peg_model='pipe'``; layout: csrc/pih_constants.h); outputs in ``obs[N,5]``, ``reward[N]``, ``done[N]``."""
 
     def __init__(self, num_envs, task="peg-in-hole", arm="panda", fly_object="banana", sub_num=None, env_id_base=0,
                  offset=(0.0, 0.0, 0.0), dt=1.0 / 240.0, solver_residual=1e-7, solver_iters=50, ik_iters=20, max_steps=0, auto_reset=False,
-                 action_frame_env=False, device=None, seed=0, kernel_family="auto", host_path=0):
+                 action_frame_env=False, device=None, seed=0, kernel_family="auto", host_path=0, peg_model="rigid"):
         L = N.lib()
         if not torch.cuda.is_available():
             raise N.PihError("peg_in_hole_gym_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else int(device))
         self.cfg = N.make_config(num_envs, task, arm, fly_object, sub_num, env_id_base, offset, dt, solver_residual,
                                  solver_iters, ik_iters, max_steps, auto_reset, action_frame_env, self.device.index, seed,
-                                 kernel_family, host_path)
+                                 kernel_family, host_path, peg_model)
         self.n = int(num_envs)
         self.action_dim = L.pih_action_dim(self.cfg.arm)
         self.obs_dim = L.pih_obs_dim()
         with torch.cuda.device(self.device):
-            self.state = torch.zeros(N.STATE_F4, self.n, 4, dtype=torch.float32, device=self.device)
+            self.state_f4 = L.pih_state_words_for(C.byref(self.cfg)) // 4       # 12 slots, 32 with the flexible pipe
+            self.state = torch.zeros(self.state_f4, self.n, 4, dtype=torch.float32, device=self.device)
             self.obs = torch.zeros(self.n, self.obs_dim, dtype=torch.float32, device=self.device)
             self.reward = torch.zeros(self.n, dtype=torch.float32, device=self.device)
             self.done = torch.zeros(self.n, dtype=torch.uint8, device=self.device)

@@ -16,13 +16,14 @@ class PihConfig(C.Structure):
                 ("sub_num", C.c_int32), ("env_id_base", C.c_int32), ("offset", C.c_float * 3), ("dt", C.c_float), ("solver_residual", C.c_float),
                 ("solver_iters", C.c_int32), ("ik_iters", C.c_int32), ("max_steps", C.c_int32),
                 ("auto_reset", C.c_int32), ("action_frame_env", C.c_int32), ("device", C.c_int32),
-                ("seed", C.c_uint64), ("kernel_family", C.c_int32), ("host_path", C.c_int32)]
+                ("seed", C.c_uint64), ("kernel_family", C.c_int32), ("host_path", C.c_int32), ("peg_model", C.c_int32)]
 
 
 def make_config(num_envs, task=0, arm=0, fly_object=0, sub_num=None, env_id_base=0, offset=(0.0, 0.0, 0.0),
                 dt=1.0 / 240.0, solver_residual=1e-7, solver_iters=50, ik_iters=20, max_steps=0, auto_reset=0, action_frame_env=0,
-                device=0, seed=0):
+                device=0, seed=0, peg_model=0):
     c = PihConfig()
+    c.peg_model = peg_model
     c.task, c.arm, c.fly_object, c.num_envs = task, arm, fly_object, num_envs
     c.sub_num = num_envs if sub_num is None else sub_num
     c.env_id_base = env_id_base
@@ -62,6 +63,7 @@ def lib():
         L.pih_oracle_rollout.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.pih_oracle_rollout_range.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 4
         L.pih_oracle_advance_global_step.argtypes = [C.c_void_p, C.c_int]
+        L.pih_oracle_state_words.argtypes = [C.POINTER(PihConfig)]
         L.pih_oracle_get_state.argtypes = [C.c_void_p, C.c_void_p]
         L.pih_oracle_set_state.argtypes = [C.c_void_p, C.c_void_p]
         L.pih_oracle_env_offset.argtypes = [C.POINTER(PihConfig), C.c_int, C.c_void_p]
@@ -85,6 +87,7 @@ def _p(a):
 
 
 STATE_WORDS = 48
+PS_POS, PS_QUAT, PS_VEL, PS_ANG, PS_GRASP, PS_QJ, PS_QDJ = 64, 67, 71, 74, 77, 80, 104      # flexible pipe block (peg_model=1)
 S_Q, S_STEP, S_EPISODE, S_FLAGS, S_QD, S_PPOS, S_PQUAT, S_PVEL, S_PANG = 0, 9, 10, 11, 12, 24, 27, 32, 35
 S_FSM_STATE, S_FSM_T, S_RANDY, S_MTGT, S_GRASP_ANG = 21, 22, 23, 40, 47
 
@@ -143,14 +146,18 @@ class Oracle:
         lib().pih_oracle_grasp_labels(self.h, width, height, lo, hi, _p(lab), _p(par))
         return lab, par
 
+    @property
+    def state_words(self):
+        return int(lib().pih_oracle_state_words(C.byref(self.cfg)))
+
     def get_state(self):
-        w = np.zeros((STATE_WORDS // 4, self.n, 4), np.float32)
+        w = np.zeros((self.state_words // 4, self.n, 4), np.float32)
         lib().pih_oracle_get_state(self.h, _p(w))
         return w
 
     def set_state(self, w):
         w = np.ascontiguousarray(w, np.float32)
-        assert w.shape == (STATE_WORDS // 4, self.n, 4)
+        assert w.shape == (self.state_words // 4, self.n, 4)
         lib().pih_oracle_set_state(self.h, _p(w))
 
 
@@ -187,3 +194,22 @@ def aba(arm, q, qd, tau, g=9.8):
     lib().pih_oracle_aba(arm, _p(np.ascontiguousarray(q, np.float64)), _p(np.ascontiguousarray(qd, np.float64)),
                          _p(np.ascontiguousarray(tau, np.float64)), g, _p(qdd), _p(minv))
     return qdd, minv
+
+
+def pipe_dyn(bquat, bvel, bang, qj, qdj, dt=1.0 / 240.0, g=9.8):
+    """(vstar[29], col[29, 29]) of the flexible pipe from the double oracle (base twist in body coordinates)."""
+    vstar, col = np.zeros(29), np.zeros((29, 29))
+    L = lib()
+    L.pih_oracle_pipe_dyn.argtypes = [C.c_void_p] * 5 + [C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    arrs = [np.ascontiguousarray(a, np.float64) for a in (bquat, bvel, bang, qj, qdj)]
+    L.pih_oracle_pipe_dyn(*[_p(a) for a in arrs], dt, g, _p(vstar), _p(col))
+    return vstar, col
+
+
+def pipe_fk(bpos, bquat, qj):
+    pos, rot = np.zeros((24, 3)), np.zeros((24, 9))
+    L = lib()
+    L.pih_oracle_pipe_fk.argtypes = [C.c_void_p] * 5
+    arrs = [np.ascontiguousarray(a, np.float64) for a in (bpos, bquat, qj)]
+    L.pih_oracle_pipe_fk(*[_p(a) for a in arrs], _p(pos), _p(rot))
+    return pos, rot.reshape(24, 3, 3)

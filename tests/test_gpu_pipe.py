@@ -1,0 +1,206 @@
+"""GPU parity of the flexible 25-link pipe (pipe.urdf, peg_in_hole.py:239-245,266,114-117): the
+warp-per-env kernels (csrc/pih_pipe.cuh) against the CPU oracle (oracle/pih_pipe_impl.h), bit for bit."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _pair(n, task="peg-in-hole", use_double=False, **kw):
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    sim = BatchedSim(n, device=0, task=task, peg_model="pipe", **kw)
+    okw = dict(kw)
+    okw["auto_reset"] = int(okw.get("auto_reset", False))
+    orc = ol.Oracle(ol.make_config(n, task={"peg-in-hole": 0, "peg-in-hole-scripted": 2}[task], peg_model=1, **okw), use_double=use_double)
+    return sim, orc
+
+
+def _state_diff(sim, orc):
+    sg, sc = sim.state.cpu().numpy(), orc.get_state()
+    assert sg.shape == sc.shape == (32, sim.n, 4)
+    bad = np.argwhere(sg.view(np.int32) != sc.view(np.int32))
+    return sg, sc, bad
+
+
+def _assert_state_equal(sim, orc, what=""):
+    sg, sc, bad = _state_diff(sim, orc)
+    if bad.size:
+        words = sorted(set(int(4 * s + c) for s, _, c in bad))
+        raise AssertionError(f"{what}: {len(bad)} state words differ; words {words[:20]} envs {sorted(set(int(e) for _, e, _ in bad))[:10]} "
+                             f"max|d|={np.nanmax(np.abs(sg - sc))}")
+
+
+def _actions(n, steps, offs, seed, kind="random"):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(steps):
+        a = rng.uniform(-1, 1, (n, 4)).astype(np.float32)
+        a[:, :3] += offs
+        out.append(a)
+    return out
+
+
+def test_pipe_reset_matches_oracle():
+    n = 64
+    sim, orc = _pair(n, offset=(2.0, 3.0, 0.0), seed=5)
+    og, oc = sim.reset().cpu().numpy(), orc.reset()
+    assert np.array_equal(og, oc)
+    _assert_state_equal(sim, orc, "reset")
+    w = orc.get_state()
+    g = ol.state_int(w, ol.PS_GRASP)
+    assert set(np.unique(g)) <= {0, 23} and len(np.unique(g)) == 2                      # random.choice([0, 23])
+    qj = ol.state_field(w, ol.PS_QJ, 23)
+    nbent = (qj != 0).sum(1)
+    assert nbent.min() >= 4 and nbent.max() <= 23 and (qj >= 0).all() and (qj <= np.pi / 3 + 1e-6).all()
+
+
+def test_pipe_drop_and_settle_200_steps_bit_exact():
+    """The pipe falls 15 cm onto the table and comes to rest on its segment contacts while the arm follows random
+    actions: ABA of the 29-dof chain, 23 joint motors, up to 36 contact points, one PGS island."""
+    n = 48
+    sim, orc = _pair(n, offset=(2.0, 3.0, 0.0), seed=11)
+    assert np.array_equal(sim.reset().cpu().numpy(), orc.reset())
+    acts = _actions(n, 200, sim.env_offsets().numpy(), 1)
+    for t, a in enumerate(acts):
+        go, gr, gd = sim.step(torch.from_numpy(a).cuda())
+        co, cr, cd = orc.step(a)
+        if t in (0, 1, 2, 5, 20, 45, 60, 100):
+            _assert_state_equal(sim, orc, f"step {t}")
+        assert np.array_equal(gd.cpu().numpy(), cd) and np.array_equal(gr.cpu().numpy(), cr), t
+        assert np.array_equal(go.cpu().numpy(), co), t
+    _assert_state_equal(sim, orc, "final")
+    flags = sim.int_word(11).cpu().numpy()
+    assert ((flags >> 8) & 1).mean() > 0.9, "the pipes rest on the table after 200 steps"
+    st = sim.state.cpu().numpy()
+    z = ol.state_field(st, ol.PS_POS, 3)[:, 2]
+    assert (z > -0.06).all() and np.isfinite(st).all()
+
+
+def test_pipe_autoreset_rollout_and_frozen_envs_bit_exact():
+    """Time limit + auto-reset (new bends, new grasp link every episode), the rollout entry point with in-kernel Philox
+    actions, and the reference's frozen-when-done behaviour (base_env.py:61-71)."""
+    n = 40
+    sim, orc = _pair(n, offset=(2.0, 3.0, 0.0), seed=3, max_steps=30, auto_reset=True)
+    assert np.array_equal(sim.reset().cpu().numpy(), orc.reset())
+    for chunk in (1, 29, 1, 40):
+        sim.rollout(chunk); orc.rollout(chunk)
+        _assert_state_equal(sim, orc, f"rollout chunk {chunk}")
+    assert np.array_equal(sim.obs.cpu().numpy(), orc.obs) and (sim.int_word(10).cpu().numpy() == 2).all()
+    torch.cuda.synchronize()
+    assert int(sim.counters[0].item()) == n * 71
+    sim2, orc2 = _pair(n, offset=(2.0, 3.0, 0.0), seed=4, max_steps=8, auto_reset=False)
+    sim2.reset(); orc2.reset()
+    acts = _actions(n, 14, sim2.env_offsets().numpy(), 2)
+    for t, a in enumerate(acts):
+        go, gr, gd = sim2.step(torch.from_numpy(a).cuda())
+        co, cr, cd = orc2.step(a)
+        assert np.array_equal(go.cpu().numpy(), co) and np.array_equal(gd.cpu().numpy(), cd), t
+    assert sim2.done.cpu().numpy().all() and (sim2.int_word(9).cpu().numpy() == 8).all()
+    _assert_state_equal(sim2, orc2, "frozen")
+
+
+def test_pipe_grasp_contacts_bit_exact():
+    """Drive the gripper onto the grasp link and close it: finger<->segment rows couple the arm's 9 and the pipe's 29
+    degrees of freedom in one solve; arm<->table rows appear when the gripper presses down."""
+    n = 32
+    sim, orc = _pair(n, offset=(2.0, 3.0, 0.0), seed=21)
+    sim.reset(); orc.reset()
+    offs = sim.env_offsets().numpy()
+    rest = np.zeros((n, 4), np.float32)
+    rest[:, :3] = offs + np.array([0.3, 0.0, 0.5], np.float32); rest[:, 3] = 0.04
+    for t in range(150):                                   # let the pipe settle first
+        sim.step(torch.from_numpy(rest).cuda()); orc.step(rest)
+    _assert_state_equal(sim, orc, "settled")
+    seen = 0
+    for t in range(260):
+        link = ol.state_field(orc.get_state(), ol.S_PPOS, 3)           # grasp link pose = state words 24..26
+        a = np.zeros((n, 4), np.float32)
+        a[:, 0:2] = link[:, :2]
+        a[:, 2] = 0.25 if t < 60 else (link[:, 2] + 0.0 if t < 170 else -0.1)
+        a[:, 3] = 0.04 if t < 150 else 0.0
+        a[:, :3] += offs
+        go, gr, gd = sim.step(torch.from_numpy(a).cuda())
+        co, cr, cd = orc.step(a)
+        assert np.array_equal(go.cpu().numpy(), co) and np.array_equal(gd.cpu().numpy(), cd), t
+        seen |= int(np.bitwise_or.reduce(sim.int_word(11).cpu().numpy() >> 8))
+        if t % 40 == 0:
+            _assert_state_equal(sim, orc, f"grasp step {t}")
+    _assert_state_equal(sim, orc, "grasp final")
+    assert seen & (4 | 8), "finger-segment contacts expected"
+    assert seen & 1
+
+
+def test_pipe_scripted_episode_bit_exact():
+    """The task the reference ships (peg_in_hole.py:39-225) on the object it ships (pipe.urdf): scripted state machine
+    reading the grasp link's pose, 2226 engine steps."""
+    n = 16
+    sim, orc = _pair(n, task="peg-in-hole-scripted", offset=(2.0, 3.0, 0.0), seed=3)
+    assert np.array_equal(sim.reset().cpu().numpy(), orc.reset())
+    for chunk in (300, 700, 700, 526):
+        sim.rollout(chunk); orc.rollout(chunk)
+        _assert_state_equal(sim, orc, f"scripted chunk {chunk}")
+    assert sim.done.cpu().numpy().all() and np.array_equal(sim.reward.cpu().numpy(), orc.reward)
+
+
+def test_pipe_nonfinite_fault_guard_and_fuzzed_states():
+    n = 64
+    sim, orc = _pair(n, offset=(2.0, 3.0, 0.0), seed=9, max_steps=40, auto_reset=True)
+    sim.reset(); orc.reset()
+    acts = _actions(n, 60, sim.env_offsets().numpy(), 7)
+    for a in acts[:20]:
+        sim.step(torch.from_numpy(a).cuda()); orc.step(a)
+    rng = np.random.default_rng(3)
+    w = orc.get_state()
+    flat = np.ascontiguousarray(w.transpose(1, 0, 2)).reshape(n, -1)
+    # fuzz: random joint angles / rates of the chain, base twist, base near the table / the hole / the gripper
+    flat[:, ol.PS_QJ:ol.PS_QJ + 23] = rng.uniform(-1.2, 1.2, (n, 23))
+    flat[:, ol.PS_QDJ:ol.PS_QDJ + 23] = rng.normal(0, 3.0, (n, 23))
+    flat[:, ol.PS_VEL:ol.PS_VEL + 3] = rng.normal(0, 1.0, (n, 3))
+    flat[:, ol.PS_ANG:ol.PS_ANG + 3] = rng.normal(0, 5.0, (n, 3))
+    q = rng.normal(size=(n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    flat[:, ol.PS_QUAT:ol.PS_QUAT + 4] = q
+    where = rng.integers(0, 3, n)
+    ee = orc.obs[:, 2:5] - sim.env_offsets().numpy()
+    pos = np.where(where[:, None] == 0, ee + rng.uniform(-0.05, 0.05, (n, 3)),
+                   np.where(where[:, None] == 1, np.array([0.5, -0.2, 0.2]) + rng.uniform(-0.05, 0.05, (n, 3)),
+                            np.stack([rng.uniform(-0.3, 0.3, n), rng.uniform(-0.7, -0.3, n), rng.uniform(-0.06, 0.05, n)], 1)))
+    flat[:, ol.PS_POS:ol.PS_POS + 3] = pos
+    bad = np.arange(5, n, 9)
+    for k, e in enumerate(bad):
+        flat[e, [ol.PS_POS + 1, ol.PS_QJ + 7, ol.PS_QUAT + 2, ol.PS_QDJ + 20][k % 4]] = np.nan
+    w2 = np.ascontiguousarray(flat.reshape(n, -1, 4).transpose(1, 0, 2)).astype(np.float32)
+    orc.set_state(w2); sim.state.copy_(torch.from_numpy(w2))
+    seen = 0
+    for t, a in enumerate(acts[20:]):
+        go, gr, gd = sim.step(torch.from_numpy(a).cuda())
+        co, cr, cd = orc.step(a)
+        assert np.array_equal(gd.cpu().numpy(), cd) and np.array_equal(gr.cpu().numpy(), cr), t
+        assert np.array_equal(go.cpu().numpy(), co), t
+        if t == 0:
+            flags = sim.int_word(11).cpu().numpy()
+            assert (flags[bad] & 4).all() and not (flags[np.setdiff1d(np.arange(n), bad)] & 4).any()
+        seen |= int(np.bitwise_or.reduce(sim.int_word(11).cpu().numpy() >> 8))
+    _assert_state_equal(sim, orc, "fuzz final")
+    assert np.isfinite(sim.state.cpu().numpy()).all() and (seen & 1)
+
+
+def test_pipe_fp32_gpu_vs_fp64_oracle_drift():
+    """north_star tolerance (1e-3 m / 1e-2 rad per step) against the double build, reported over 100 steps of free fall,
+    impact and settling (contact-rich chaotic phases decorrelate afterwards; the bound is asserted on the horizon where
+    both engines still follow the same contact sequence)."""
+    n = 32
+    sim, orc = _pair(n, use_double=True, offset=(2.0, 3.0, 0.0), seed=13)
+    sim.reset(); orc.reset()
+    acts = _actions(n, 60, sim.env_offsets().numpy(), 12)
+    worst_q = worst_p = 0.0
+    for t, a in enumerate(acts):
+        sim.step(torch.from_numpy(a).cuda()); orc.step(a)
+        sg, sc = sim.state.cpu().numpy(), orc.get_state()
+        worst_q = max(worst_q, np.abs(ol.state_field(sg, ol.PS_QJ, 23) - ol.state_field(sc, ol.PS_QJ, 23)).max(),
+                      np.abs(ol.state_field(sg, ol.S_Q, 9) - ol.state_field(sc, ol.S_Q, 9)).max())
+        worst_p = max(worst_p, np.abs(ol.state_field(sg, ol.PS_POS, 3) - ol.state_field(sc, ol.PS_POS, 3)).max())
+    print(f"pipe: fp32 GPU vs fp64 oracle over 60 steps: max |dq| = {worst_q:.3e} rad, max |dpos| = {worst_p:.3e} m")
+    assert worst_q < 1e-2 and worst_p < 1e-3
