@@ -245,6 +245,26 @@ def contact_rich_probe(n, local, torch, barrier):
     return out
 
 
+def pipe_probe(n, local, torch, barrier):
+    """The reference's own peg (pipe.urdf: 25 links, 23 continuous joints) at n envs: microseconds per
+    env.step of the warp-per-env kernels over a whole 200-step episode window (fall, impact, settling, arm random)."""
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    sim = BatchedSim(n, peg_model="pipe", sub_num=n, offset=OFFSET, seed=SEED, max_steps=MAX_STEPS, auto_reset=True, device=local)
+    sim.reset()
+    sim.rollout(10, count=False)
+    st = sim.stats()
+    steps = 200
+    ms = timed_steps(lambda i: sim.rollout(steps, count=False), 1, barrier, torch)
+    v = st.cpu().numpy().astype(float)
+    sim.stats(False)
+    es = max(v[0], 1.0)
+    out = {"envs": n, "us_per_step": 1e3 * ms / steps, "env_steps_per_s": n * steps / (ms * 1e-3), "launches_per_step": 2,
+           "kernels": "pih::k_pipe_arm (thread per env) + pih::k_pipe_step (warp per env)", "dof": "9 arm + 29 pipe",
+           "contacts_mean": v[4] / es, "pgs_iters_mean": v[3] / es, "pgs_row_iters_mean": v[2] / es, "ik_iters_mean": v[1] / es, "faults": v[6]}
+    sim.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -447,9 +467,10 @@ def main():
     sim_st.close()
 
     dev_ms, roll_ms, e2e_s, staged_s = reduce_max(dev_ms), reduce_max(roll_ms), reduce_max(e2e_s), reduce_max(staged_s)
-    contact_rich = None
+    contact_rich = pipe = None
     if world == 1 and args.task == "peg-in-hole" and args.arm == "panda":
         contact_rich = contact_rich_probe(n, local, torch, barrier)
+        pipe = pipe_probe(n, local, torch, barrier)
     for sm in sims:
         sm.close()
     if peer is not None:
@@ -521,7 +542,7 @@ def main():
                                  "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"}},
             "cpu_baseline": cpu,
             "extra": {"rollout_single_launch_value": total_envs * args.steps / (roll_ms * 1e-3),
-                      "wall_s_timed_region": t_wall, "contact_rich": contact_rich, "config5": config5},
+                      "wall_s_timed_region": t_wall, "contact_rich": contact_rich, "flexible_pipe": pipe, "config5": config5},
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
