@@ -13,6 +13,7 @@
 /* diagnostics only (not thread-safe counters; approximate under threads) */
 unsigned long long pih_dbg_pgs_iters = 0, pih_dbg_pgs_steps = 0;
 
+/* (set by pih_oracle_capture_step; read by step_env) */
 #define REAL float
 #define SUFFIX _f
 #define REAL_IS_DOUBLE 0
@@ -477,3 +478,20 @@ void pih_oracle_pipe_fk(const double* bpos, const double* bquat, const double* q
     for (int i = 0; i < 9; ++i) rot[9 * b + i] = K.Rw[b].m[i / 3][i % 3];
   }
 }
+
+
+/* test hook: steps env `i` once with `action` and returns the assembled problem + solution of that step (see pih_capture) */
+pih_capture* pih_dbg_capture = 0;
+int pih_oracle_capture_step(void* h, int i, const float* action, pih_capture* out) {
+  oracle* o = (oracle*)h;
+  if (o->cfg.peg_model == PIH_PEG_PIPE) return PIH_ERR_INVALID;
+  float a[6] = {0, 0, 0, 0, 0, 0}, ob[5], rw;
+  uint8_t dn;
+  int A = (o->cfg.arm == PIH_ARM_PANDA) ? 4 : 6;
+  for (int k = 0; k < A; ++k) a[k] = action[k];
+  pih_dbg_capture = out;
+  step_one(o, i, a, ob, &rw, &dn);
+  pih_dbg_capture = 0;
+  return 0;
+}
+int pih_oracle_capture_size(void) { return (int)sizeof(pih_capture); }

@@ -24,6 +24,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
 
 #ifndef REAL
 #error "define REAL, SUFFIX and REAL_IS_DOUBLE before including"
@@ -740,10 +741,26 @@ static inline int FN(fb_sample)(const model* M, int k, v3* pl) {
   return 1;
 }
 
+/* FSM state of THIS step (update_state runs before the constraint is created / removed and before stepSimulation,
+ * peg_in_hole.py:55,99-108): the grasp constraint exists while the state is 4, 5 or 6 */
+static inline int FN(grasp_active)(const simcfg* C, int fsm_state_now) {
+  return C->task == PIH_TASK_SCRIPTED && fsm_state_now >= PIH_FSM_GRASP_FIRST && fsm_state_now <= PIH_FSM_GRASP_LAST;
+}
+
 static void FN(collide)(const model* M, const simcfg* C, const envstate* S, const fkres* F, const m3* Rfb, contactset* CS) {
   CS->n = 0;
   v3 pfb = FN(v3_make)(S->ppos[0], S->ppos[1], S->ppos[2]);
   contact c;
+  /* (0) grasp constraint of the scripted task: a pseudo contact whose three rows are bilateral and run along the env axes.
+   *     p = end-effector origin (the pin point on both bodies), n carries the position error child point - parent point. */
+  if (FN(grasp_active)(C, S->fsm_state)) {
+    v3 pee; m3 Ree;
+    FN(ee_pose)(M, F, &pee, &Ree);
+    v3 pc = FN(m3_v_add)(Rfb, FN(v3_make)(RC(0), S->rand_y, RC(0)), pfb);
+    c.pair = PIH_PAIR_GRASP; c.has_fb = 1; c.arm_body = M->ee_body; c.p = pee; c.n = FN(v3_sub)(pc, pee);
+    c.dist = RC(-1e30); c.mu = RC(-1);
+    FN(contact_push)(CS, &c);
+  }
   /* (1) free body vs table plane z = PIH_TABLE_Z */
   if (M->fb_shape == 0) {
     v3 ax = FN(m3_col)(Rfb, 1);
@@ -894,6 +911,27 @@ static inline v3 FN(clamp_norm)(v3 v) {
   if (n2 > RC(PIH_MAX_COORD_VEL * PIH_MAX_COORD_VEL)) return FN(v3_scale)(v, RC(PIH_MAX_COORD_VEL) / SQRT(n2));
   return v;
 }
+
+/* ------------------------------------------------------------------ test hook: the assembled velocity-level problem
+ * of one env.step (rows, bounds, targets, M^-1, v*) and the solver's answer, for an INDEPENDENT check of the solution
+ * (tests/test_oracle_lcp.py verifies the complementarity conditions and re-solves the box QP densely in numpy). */
+#ifndef PIH_ORACLE_CAPTURE
+#define PIH_ORACLE_CAPTURE
+#define PIH_CAP_MAXR (3 * PIH_NB_MAX + 3 * PIH_MAXC)
+#define PIH_CAP_NV (PIH_NB_MAX + 6)
+typedef struct {
+  int nrows, nv;
+  double J[PIH_CAP_MAXR][PIH_CAP_NV];   /* generalized velocity = (arm joint rates[nb], free-body linear[3], angular[3]) */
+  double tv[PIH_CAP_MAXR];              /* target row velocity */
+  double lo[PIH_CAP_MAXR], hi[PIH_CAP_MAXR];   /* impulse bounds; friction rows: hi = mu, lo = index of their normal row, kind = 1 */
+  int kind[PIH_CAP_MAXR];               /* 0 box-bounded, 1 friction (|lambda| <= mu * lambda[normal]) */
+  double lam[PIH_CAP_MAXR];
+  double Minv[PIH_CAP_NV][PIH_CAP_NV];
+  double vstar[PIH_CAP_NV], vplus[PIH_CAP_NV];
+  int iters;
+} pih_capture;
+extern pih_capture* pih_dbg_capture;
+#endif
 
 /* ------------------------------------------------------------------ one env.step */
 typedef struct {
@@ -1298,8 +1336,9 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
     crow* r = &rows[k];
     pairmask |= c->pair;
     r->has_fb = c->has_fb; r->arm_body = c->arm_body; r->mu = c->mu;
-    r->dir[0] = c->n;
-    FN(plane_space)(c->n, &r->dir[1], &r->dir[2]);
+    const int weld = c->pair == PIH_PAIR_GRASP;
+    if (weld) { r->dir[0] = FN(v3_make)(1, 0, 0); r->dir[1] = FN(v3_make)(0, 1, 0); r->dir[2] = FN(v3_make)(0, 0, 1); }
+    else { r->dir[0] = c->n; FN(plane_space)(c->n, &r->dir[1], &r->dir[2]); }
     v3 rr = FN(v3_sub)(c->p, pfb);
     for (int d = 0; d < 3; ++d) {
       real diag = RC(0), vrel = RC(0);
@@ -1335,7 +1374,8 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
       r->dinv[d] = RC(1) / diag;
       r->diag[d] = diag;
       real tv = RC(0);
-      if (d == 0) tv = (c->dist > RC(0)) ? -(c->dist * idt) : -(RC(PIH_ERP) * c->dist * idt);
+      if (weld) tv = -(RC(PIH_ERP) * (d == 0 ? c->n.x : (d == 1 ? c->n.y : c->n.z)) * idt);
+      else if (d == 0) tv = (c->dist > RC(0)) ? -(c->dist * idt) : -(RC(PIH_ERP) * c->dist * idt);
       r->b[d] = (tv - vrel) * r->dinv[d];
       r->lam[d] = RC(0);
     }
@@ -1351,9 +1391,10 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
    * merges them into one island. */
   int coupled = 0;
   for (int k = 0; k < CS.n; ++k) if (rows[k].has_fb && rows[k].arm_body >= 0) coupled = 1;
-  int arm_on = 1, fb_on = 1;
+  int arm_on = 1, fb_on = 1, it_done_ = 0;
   for (int it = 0; it < C->solver_iters; ++it) {
     real res_a = RC(0), res_f = RC(0);
+    it_done_ = it + 1;
 #define PIH_RES(acc_, dl_, diag_) do { real rv_ = (dl_) * (diag_); rv_ = rv_ * rv_; if (rv_ > acc_) acc_ = rv_; } while (0)
     /* Accumulated-impulse projection of one row (btMultiBodyConstraintSolver::resolveSingleConstraintRowGeneric [3P]:
      * sum = applied + delta, clamped to [lower, upper]).  Stated on the delta: delta is clamped to
@@ -1396,7 +1437,10 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
             rel = r->has_fb ? rel + (s0 + s1) : (s0 + s1);
           }
           real dl = FMA(-rel, r->dinv[d], r->b[d]);
-          if (d == 0) PIH_PROJECT_LO(dl, r->lam[d]);
+          if (r->mu < RC(0)) {                     /* grasp constraint: bilateral, |impulse| <= maxForce dt */
+            const real wl = RC(PIH_GRASP_MAX_FORCE) * dt;
+            PIH_PROJECT(dl, r->lam[d], -wl, wl);
+          } else if (d == 0) PIH_PROJECT_LO(dl, r->lam[d]);
           else {
             real lim = r->mu * r->lam[0];
             PIH_PROJECT(dl, r->lam[d], -lim, lim);
@@ -1419,6 +1463,65 @@ static int FN(step_env)(const model* M, const simcfg* C, envstate* S, const real
     }
   }
   pih_dbg_pgs_steps += 1;
+  if (pih_dbg_capture) {
+    pih_capture* Q = pih_dbg_capture;
+    memset(Q, 0, sizeof(*Q));
+    const int nv = nb + 6;
+    Q->nv = nv;
+    int R = 0;
+    for (int j = 0; j < nb; ++j) {             /* motors: v_j = v*_target, |lambda| <= maxForce dt */
+      real qt = qstar[j];
+      qt = (qt < M->lo[j]) ? M->lo[j] : ((qt > M->hi[j]) ? M->hi[j] : qt);
+      Q->J[R][j] = 1.0; Q->tv[R] = (double)(kpc[j] * (qt - S->q[j]) * idt); Q->lo[R] = -(double)m_max[j]; Q->hi[R] = (double)m_max[j];
+      Q->lam[R] = (double)m_lam[j]; R++;
+    }
+    for (int j = 0; j < nb; ++j)
+      for (int side = 0; side < 2; ++side) {
+        if (!l_on[side][j]) continue;
+        real glo = S->q[j] - M->lo[j], ghi = M->hi[j] - S->q[j];
+        real g_ = side ? ghi : glo;
+        Q->J[R][j] = side ? -1.0 : 1.0;
+        Q->tv[R] = (double)((g_ > RC(0)) ? -(g_ * idt) : -(RC(PIH_ERP) * g_ * idt));
+        Q->lo[R] = 0.0; Q->hi[R] = 1e300; Q->lam[R] = (double)l_lam[side][j]; R++;
+      }
+    int nrow0[PIH_MAXC];
+    for (int pass = 0; pass < 2; ++pass)
+      for (int k = 0; k < CS.n; ++k) {
+        crow* r = &rows[k];
+        for (int d = (pass ? 1 : 0); d < (pass ? 3 : 1); ++d) {
+          if (r->arm_body >= 0) for (int j = 0; j < nb; ++j) Q->J[R][j] = (double)r->ja[d][j];
+          if (r->has_fb) {
+            Q->J[R][nb + 0] = (double)r->dir[d].x; Q->J[R][nb + 1] = (double)r->dir[d].y; Q->J[R][nb + 2] = (double)r->dir[d].z;
+            Q->J[R][nb + 3] = (double)r->jang[d].x; Q->J[R][nb + 4] = (double)r->jang[d].y; Q->J[R][nb + 5] = (double)r->jang[d].z;
+          }
+          Q->tv[R] = (double)(r->b[d] * r->diag[d]) + 0.0;   /* b = (tv - J v*) / diag  ->  tv = b diag + J v* (added below) */
+          if (r->mu < RC(0)) { Q->lo[R] = -(double)(RC(PIH_GRASP_MAX_FORCE) * dt); Q->hi[R] = -Q->lo[R]; }
+          else if (d == 0) { Q->lo[R] = 0.0; Q->hi[R] = 1e300; nrow0[k] = R; }
+          else { Q->kind[R] = 1; Q->lo[R] = (double)nrow0[k]; Q->hi[R] = (double)r->mu; }
+          Q->lam[R] = (double)r->lam[d];
+          R++;
+        }
+      }
+    Q->nrows = R;
+    for (int i = 0; i < nb; ++i) {
+      Q->vstar[i] = (double)vs[i]; Q->vplus[i] = (double)(vs[i] + dva[i]);
+      for (int j = 0; j < nb; ++j) Q->Minv[i][j] = (double)Minv[i][j];
+    }
+    real fvv[3] = {fv.x, fv.y, fv.z}, fww[3] = {fw.x, fw.y, fw.z}, dl3[3] = {dvl.x, dvl.y, dvl.z}, dw3[3] = {dvw.x, dvw.y, dvw.z};
+    for (int k = 0; k < 3; ++k) {
+      Q->vstar[nb + k] = (double)fvv[k]; Q->vstar[nb + 3 + k] = (double)fww[k];
+      Q->vplus[nb + k] = (double)(fvv[k] + dl3[k]); Q->vplus[nb + 3 + k] = (double)(fww[k] + dw3[k]);
+      Q->Minv[nb + k][nb + k] = (double)im;
+      for (int c2 = 0; c2 < 3; ++c2) Q->Minv[nb + 3 + k][nb + 3 + c2] = (double)Iinv.m[k][c2];
+    }
+    /* contact / constraint rows (the last 3 per contact) stored b = (tv - J v*) / diag: recover tv */
+    for (int r2 = R - 3 * CS.n; r2 < R; ++r2) {
+      double jv = 0.0;
+      for (int c2 = 0; c2 < nv; ++c2) jv += Q->J[r2][c2] * Q->vstar[c2];
+      Q->tv[r2] += jv;
+    }
+    Q->iters = it_done_;
+  }
   /* ---- integrate (semi-implicit Euler) ---- */
   for (int j = 0; j < nb; ++j) {
     real v = vs[j] + dva[j];

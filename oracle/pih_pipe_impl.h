@@ -601,6 +601,20 @@ static int FN(step_env_pipe)(const model* M, const pipemodel* PM, const simcfg* 
    *      involve the arm (later ones are dropped). */
   pcontact con[PIH_PIPE_MAXC];
   int ncon = 0, narmc = 0, pairmask = 0;
+  if (FN(grasp_active)(C, S->fsm_state)) {
+    /* grasp constraint of the scripted task (peg_in_hole.py:99-104; see PIH_PAIR_GRASP): the grasp link's point
+     * random_vector is pinned to the end-effector origin - first row set of the step, bilateral, along the env axes */
+    v3 pee; m3 Ree;
+    FN(ee_pose)(M, &F, &pee, &Ree);
+    m3 Rg = FN(quat_to_m3)(S->pquat);
+    v3 pc = FN(m3_v_add)(&Rg, FN(v3_make)(RC(0), S->rand_y, RC(0)), FN(v3_make)(S->ppos[0], S->ppos[1], S->ppos[2]));
+    pcontact c;
+    c.pair = PIH_PAIR_GRASP; c.seg = (PS->grasp_idx == 0) ? 1 : PIH_PIPE_NSEG - 1; c.arm_body = M->ee_body;
+    c.p = pee; c.n = FN(v3_sub)(pc, pee); c.dist = RC(-1e30); c.mu = RC(-1);
+    con[ncon++] = c;
+    narmc += 1;
+  }
+  const int nweld = ncon;
   {
     pcontact slots[PIH_PIPE_NSEG][PIH_PIPE_SEG_MAXC];
     int cnt[PIH_PIPE_NSEG];
@@ -610,7 +624,7 @@ static int FN(step_env_pipe)(const model* M, const pipemodel* PM, const simcfg* 
     }
     for (int k = 0; k < PIH_PIPE_SEG_MAXC; ++k)
       for (int s = 0; s < PIH_PIPE_NSEG; ++s) {
-        if (k >= cnt[s] || ncon >= PIH_PIPE_SEG_TOTAL) continue;
+        if (k >= cnt[s] || ncon - nweld >= PIH_PIPE_SEG_TOTAL) continue;
         if (slots[s][k].arm_body >= 0) { if (narmc >= PIH_PIPE_ARMROWS) continue; narmc += 1; }
         con[ncon++] = slots[s][k];
       }
@@ -642,8 +656,9 @@ static int FN(step_env_pipe)(const model* M, const pipemodel* PM, const simcfg* 
     pairmask |= c->pair;
     r->has_pipe = c->seg >= 0; r->has_arm = c->arm_body >= 0; r->mu = c->mu;
     v3 dir[3];
-    dir[0] = c->n;
-    FN(plane_space)(c->n, &dir[1], &dir[2]);
+    const int weld = c->pair == PIH_PAIR_GRASP;
+    if (weld) { dir[0] = FN(v3_make)(1, 0, 0); dir[1] = FN(v3_make)(0, 1, 0); dir[2] = FN(v3_make)(0, 0, 1); }
+    else { dir[0] = c->n; FN(plane_space)(c->n, &dir[1], &dir[2]); }
     for (int d = 0; d < 3; ++d) {
       if (r->has_pipe) {
         const int L = PIPE_SEG_BODY(c->seg);
@@ -694,7 +709,8 @@ static int FN(step_env_pipe)(const model* M, const pipemodel* PM, const simcfg* 
       r->dinv[d] = RC(1) / diag;
       r->diag[d] = diag;
       real tv = RC(0);
-      if (d == 0) tv = (c->dist > RC(0)) ? -(c->dist * idt) : -(RC(PIH_ERP) * c->dist * idt);
+      if (weld) tv = -(RC(PIH_ERP) * (d == 0 ? c->n.x : (d == 1 ? c->n.y : c->n.z)) * idt);
+      else if (d == 0) tv = (c->dist > RC(0)) ? -(c->dist * idt) : -(RC(PIH_ERP) * c->dist * idt);
       r->b[d] = (tv - vrel) * r->dinv[d];
       r->lam[d] = RC(0);
     }
@@ -746,7 +762,10 @@ static int FN(step_env_pipe)(const model* M, const pipemodel* PM, const simcfg* 
           }
           real rel = FN(bfly32)(pp);
           real dl = FMA(-rel, r->dinv[d], r->b[d]);
-          if (d == 0) PIH_PROJECT_LO(dl, r->lam[d]);
+          if (r->mu < RC(0)) {                     /* grasp constraint: bilateral, |impulse| <= maxForce dt */
+            const real wl = RC(PIH_GRASP_MAX_FORCE) * dt;
+            PIH_PROJECT(dl, r->lam[d], -wl, wl);
+          } else if (d == 0) PIH_PROJECT_LO(dl, r->lam[d]);
           else {
             real lim = r->mu * r->lam[0];
             PIH_PROJECT(dl, r->lam[d], -lim, lim);

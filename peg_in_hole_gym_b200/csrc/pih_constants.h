@@ -109,7 +109,7 @@
 #define PIH_PIPE_ARM_MAXC 4     /* arm-sphere <-> table contacts kept per step (deepest first) */
 #define PIH_PIPE_SEG_TOTAL 32   /* pipe contact points solved per step: every segment's deeper point first (segment order), then the
                                    second points, until 32 (a pipe lying flat keeps 25 + 7) */
-#define PIH_PIPE_MAXC (PIH_PIPE_SEG_TOTAL + PIH_PIPE_ARM_MAXC)
+#define PIH_PIPE_MAXC (PIH_PIPE_SEG_TOTAL + PIH_PIPE_ARM_MAXC + 1)   /* + the scripted task's grasp constraint */
 #define PIH_PIPE_ARMROWS 16     /* of those, contact points that involve the arm (finger / arm sphere <-> segment, arm <-> table):
                                    later ones are dropped */
 /* pipe task state: float4 slots 16..31 of a PIH_PIPE_STATE_F4-slot buffer (slots 0..11 as above, 12..15 reserved) */
@@ -122,7 +122,16 @@
 #define PIH_PS_GRASP (PIH_PS_BASE + 13) /* int bits: grasp_joint_idx, 0 or 23 (peg_in_hole.py:266) */
 #define PIH_PS_QJ (PIH_PS_BASE + 16)    /* 23 joint angles */
 #define PIH_PS_QDJ (PIH_PS_BASE + 40)   /* 23 joint rates */
-#define PIH_PAIR_PIPE_SELF 64    /* (reserved) */
+#define PIH_PAIR_GRASP 64       /* the scripted task's grasp constraint (peg_in_hole.py:99-104) is active */
+/* createConstraint(panda, 11, object, grasp_joint_idx, JOINT_GEAR, [0,0,0], [0,0,0], random_vector, childFrameOrientation) on
+ * entering FSM state 4, removeConstraint on entering state 7 (peg_in_hole.py:99-104).  What Bullet's gear constraint makes
+ * of these arguments cannot be established ([3P]: link 11 hangs on a FIXED joint and owns no degree of freedom for a gear
+ * row).  Built here is the evident intent - the object's grasp point (child frame position = random_vector) is pinned to the
+ * end-effector origin (parent frame position [0,0,0]) while the constraint exists: three bilateral velocity rows along the
+ * env axes, position error corrected with ERP, |force| <= createConstraint's default maxForce 500 N per row.  NEW. */
+#define PIH_GRASP_MAX_FORCE 500.0
+#define PIH_FSM_GRASP_FIRST 4
+#define PIH_FSM_GRASP_LAST 6
 
 /* random-fly free bodies (assets/urdf/banana.urdf:5-15; Amicelli_800_tex.urdf:5-15): mass 1, mu 0;
  * collision = AABB box of the convex pieces */

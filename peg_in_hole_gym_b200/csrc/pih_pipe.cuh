@@ -885,6 +885,21 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_step(S
     float pm_lam = 0.0f;
     // ---- contacts: lane s owns segment s; then the slot-major compaction the oracle defines
     int ncon = 0, narmc = 0, pairmask = 0;
+    if (TASK == PIH_TASK_SCRIPTED && grasp_active(TASK, S.fsm_state)) {
+      // grasp constraint of the scripted task (peg_in_hole.py:99-104): first row set, bilateral, along the env axes
+      FK<ARM> Fa;
+      fk<ARM, nb>(S.q, Fa);
+      v3 pee; m3 Ree;
+      ee_pose<ARM>(Fa, pee, Ree);
+      m3 Rg = quat_to_m3(S.pquat);
+      v3 pc = mv_add(Rg, mk(0.0f, S.rand_y, 0.0f), mk(S.ppos[0], S.ppos[1], S.ppos[2]));
+      PContact c;
+      c.pair = PIH_PAIR_GRASP; c.seg = (B.grasp_idx == 0) ? 1 : PNSEG - 1; c.arm_body = ArmDims<ARM>::EE;
+      c.p = pee; c.n = vsub(pc, pee); c.dist = -1e30f; c.mu = -1.0f;
+      contact_store(sm, 0, c, 0);
+      ncon = 1; narmc = 1;
+    }
+    const int nweld = ncon;
     {
       PContact slot[PIH_PIPE_SEG_MAXC];
       int cnt = 0;
@@ -901,7 +916,7 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_step(S
         const unsigned mh = __ballot_sync(FULL, have), ma = __ballot_sync(FULL, arm);
         int my_idx = -1, my_arm = -1;
         for (int s = 0; s < PNSEG; ++s) {
-          if (!((mh >> s) & 1u) || ncon >= PIH_PIPE_SEG_TOTAL) continue;
+          if (!((mh >> s) & 1u) || ncon - nweld >= PIH_PIPE_SEG_TOTAL) continue;
           const bool a = (ma >> s) & 1u;
           if (a && narmc >= PIH_PIPE_ARMROWS) continue;
           if (s == lane) { my_idx = ncon; my_arm = a ? narmc : -1; }
@@ -966,8 +981,9 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_step(S
       pairmask |= cpair;
       const bool has_pipe = cseg >= 0, has_arm = carm >= 0;
       v3 dir[3];
-      dir[0] = cn;
-      plane_space(cn, dir[1], dir[2]);
+      const bool weld = TASK == PIH_TASK_SCRIPTED && cpair == PIH_PAIR_GRASP;
+      if (weld) { dir[0] = mk(1.0f, 0.0f, 0.0f); dir[1] = mk(0.0f, 1.0f, 0.0f); dir[2] = mk(0.0f, 0.0f, 1.0f); }
+      else { dir[0] = cn; plane_space(cn, dir[1], dir[2]); }
       const int Lb = has_pipe ? seg_body(cseg) : 0;
       const unsigned anc = has_arm ? T.anc[carm] : 0u;
 #pragma unroll
@@ -1014,7 +1030,8 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_step(S
         const float diag = bfly32(pd), vrel = bfly32(pv);
         const float dinv = 1.0f / diag;
         float tv = 0.0f;
-        if (d == 0) tv = (cdist > 0.0f) ? -(cdist * idt) : -((float)PIH_ERP * cdist * idt);
+        if (weld) tv = -((float)PIH_ERP * (d == 0 ? cn.x : (d == 1 ? cn.y : cn.z)) * idt);
+        else if (d == 0) tv = (cdist > 0.0f) ? -(cdist * idt) : -((float)PIH_ERP * cdist * idt);
         float* rs = &sm[SM_ROWS + 4 * r];
         rs[0] = dinv; rs[1] = diag; rs[2] = (tv - vrel) * dinv; rs[3] = 0.0f;      // (every lane writes the same values)
       }
@@ -1110,7 +1127,12 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_step(S
             float* rs = &sm[SM_ROWS + 4 * r];
             float dl = fmaf(-rel, rs[0], rs[2]);
             const float lam = rs[3];
-            if (d == 0) {
+            if (TASK == PIH_TASK_SCRIPTED && mu < 0.0f) {   // grasp constraint: bilateral, |impulse| <= maxForce dt
+              const float wl = (float)PIH_GRASP_MAX_FORCE * dt;
+              const float dlo = -wl - lam, dhi = wl - lam;
+              dl = (dl < dlo) ? dlo : dl;
+              dl = (dl > dhi) ? dhi : dl;
+            } else if (d == 0) {
               const float dlo = -lam;
               dl = (dl < dlo) ? dlo : dl;
             } else {

@@ -130,11 +130,36 @@ template <int TASK> PIH_D bool fb_sample(const SimParams& P, int k, v3& pl) {
   return true;
 }
 
-template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvState& S, const FK<ARM>& F, const m3& Rfb, ContactSet& CS) {
+// FSM state of THIS step as the dynamics sees it (update_state runs before the constraint is created / removed and before
+// stepSimulation, peg_in_hole.py:55,99-108).  `advanced`: S already holds the updated state (apply_action ran in this thread).
+template <int TASK> PIH_D int fsm_state_now(const EnvState& S, bool advanced) {
+  if (TASK != PIH_TASK_SCRIPTED) return 0;
+  if (advanced) return S.fsm_state;
+  const int fsm_steps[PIH_FSM_NSTATES] = {PIH_FSM_STEPS_LIST};
+  int lim = 0;
+#pragma unroll
+  for (int k = 0; k < PIH_FSM_NSTATES; ++k) lim = (S.fsm_state == k) ? fsm_steps[k] : lim;
+  int st = S.fsm_state;
+  if (S.fsm_t == lim) { st += 1; if (st >= PIH_FSM_NSTATES) st = 0; }
+  return st;
+}
+PIH_D bool grasp_active(int task, int fsm_now) { return task == PIH_TASK_SCRIPTED && fsm_now >= PIH_FSM_GRASP_FIRST && fsm_now <= PIH_FSM_GRASP_LAST; }
+
+template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvState& S, const FK<ARM>& F, const m3& Rfb, int fsm_now, ContactSet& CS) {
   const ArmTables& T = c_arm[ARM];
   CS.n = 0;
   v3 pfb = mk(S.ppos[0], S.ppos[1], S.ppos[2]);
   Contact c;
+  // (0) grasp constraint of the scripted task (peg_in_hole.py:99-104; PIH_PAIR_GRASP in pih_constants.h): a pseudo contact
+  //     whose three rows are bilateral and run along the env axes; p = end-effector origin, n carries the position error
+  if (TASK == PIH_TASK_SCRIPTED && grasp_active(TASK, fsm_now)) {
+    v3 pee; m3 Ree;
+    ee_pose<ARM>(F, pee, Ree);
+    v3 pc = mv_add(Rfb, mk(0.0f, S.rand_y, 0.0f), pfb);
+    c.pair = PIH_PAIR_GRASP; c.has_fb = 1; c.arm_body = ArmDims<ARM>::EE; c.p = pee; c.n = vsub(pc, pee);
+    c.dist = -1e30f; c.mu = -1.0f;
+    contact_push(CS, c);
+  }
   const float mu_static = P.fb_mu * (float)PIH_MU_DEFAULT;
   // (1) free body vs table plane
   if (pfb.z - (float)PIH_TABLE_Z < 0.25f) {  // cheap cull: nothing of the body is near the table (exact no-op otherwise)

@@ -15,6 +15,7 @@ CASES = {
     "panda_peg": dict(task=0, arm=0, offset=(2.0, 3.0, 0.0), seed=42, max_steps=80, auto_reset=1),
     "ur5_peg": dict(task=0, arm=1, offset=(2.0, 3.0, 0.0), seed=43, max_steps=80, auto_reset=1),
     "panda_fly": dict(task=1, arm=0, fly_object=0, dt=1.0 / 120.0, offset=(2.0, 3.0, 0.0), seed=44, max_steps=100, auto_reset=1),
+    "panda_pipe": dict(task=0, arm=0, peg_model=1, offset=(2.0, 3.0, 0.0), seed=45, max_steps=90, auto_reset=1),   # the 25-link pipe.urdf chain
 }
 N, STEPS = 8, 200
 

@@ -404,7 +404,7 @@ def test_full_size_properties_4096_envs():
     assert int(a.counters[0].item()) == n * 210
 
 
-@pytest.mark.parametrize("case", ["panda_peg", "ur5_peg", "panda_fly"])
+@pytest.mark.parametrize("case", ["panda_peg", "ur5_peg", "panda_fly", "panda_pipe"])
 def test_cuda_path_reproduces_golden_fixtures(case):
     """Committed fixtures (tests/golden/, generated by gen_golden.py from the oracle): CUDA path must match them."""
     import os
@@ -416,6 +416,8 @@ def test_cuda_path_reproduces_golden_fixtures(case):
     if "fly_object" in kw:
         kw["fly_object"] = {0: "banana", 1: "amicelli"}[kw["fly_object"]]
     kw["auto_reset"] = bool(kw["auto_reset"])
+    if "peg_model" in kw:
+        kw["peg_model"] = {0: "rigid", 1: "pipe"}[kw["peg_model"]]
     sim = _sim(N, task=task, arm=arm, **kw)
     assert np.array_equal(sim.reset().cpu().numpy(), g["obs0"])
     for t in range(STEPS):

@@ -165,7 +165,7 @@ def test_success_reward_when_peg_is_at_the_hole():
     assert r[0] == 1.0 and d[0] == 1 and r[1] == 0.0 and d[1] == 0           # peg_in_hole.py:114-117
 
 
-@pytest.mark.parametrize("case", ["panda_peg", "ur5_peg", "panda_fly"])
+@pytest.mark.parametrize("case", ["panda_peg", "ur5_peg", "panda_fly", "panda_pipe"])
 def test_oracle_reproduces_golden_fixtures(case):
     from golden.gen_golden import CASES, N, STEPS
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", case + ".npz"))
