@@ -66,7 +66,7 @@ typedef struct pih_handle pih_handle;
 /* ABI / layout queries */
 int pih_abi_version(void);
 int pih_state_words(void);                 /* 32-bit words of state per env (= 4 * float4 slots), rigid peg model */
-int pih_state_words_for(const pih_config* cfg);   /* the same for any config: 48, or 128 with peg_model = 1 */
+int pih_state_words_for(const pih_config* cfg);   /* the same for any config: 48; 64 for the scripted task (+ latched grasp scene); 128 with peg_model = 1 */
 int pih_action_dim(int arm);               /* 4 panda (peg_in_hole.py:12), 6 ur5 (utils.py:70-72) */
 int pih_obs_dim(void);                     /* 5 (peg_in_hole.py:13) */
 
@@ -129,6 +129,11 @@ int pih_ee_pose(pih_handle* h, float* pos_dev, float* rot_dev, void* stream);
  * near 0.001, far 1000.  rgbd_dev float[num_envs][height][width][4] = (OpenGL depth buffer value, r, g, b in 0..255),
  * the layout of the reference's np.concatenate((depth, rgb), 2).  The reference renders 300 x 300. */
 int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, void* stream);
+
+/* Scripted task only: the same camera on the scene LATCHED when the grasp state machine entered state 2 - the reference's
+ * `self.grasp_img = self.render()` (peg_in_hole.py:65-66), the observation the shipped get_info returns (peg_in_hole.py:33-37)
+ * together with the label images below.  Envs that have not reached state 2 yet show the present scene. */
+int pih_render_grasp(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, void* stream);
 
 /* The label images of the shipped task's random_grasp (peg_in_hole.py:41-45,65-98), for every env: a rotated
  * rectangle (half extents 0.1 x 0.2 in normalised image units; angle captured by the scripted state machine when it

@@ -212,12 +212,17 @@ void pih_oracle_last_contacts(void* h, int* out) {
 
 /* state exchange in the device layout: words[slot][env][4] (float4 SoA, pih_constants.h) */
 #define WIDX(w, i, n) ((size_t)((w) >> 2) * (size_t)(n) * 4 + (size_t)(i) * 4 + ((w) & 3))
-int pih_oracle_state_words(const pih_config* cfg) { return cfg->peg_model == PIH_PEG_PIPE ? 4 * PIH_PIPE_STATE_F4 : PIH_STATE_WORDS; }
+int pih_oracle_state_words(const pih_config* cfg) {
+  return cfg->peg_model == PIH_PEG_PIPE ? 4 * PIH_PIPE_STATE_F4 : (cfg->task == PIH_TASK_SCRIPTED ? 4 * PIH_SCRIPTED_STATE_F4 : PIH_STATE_WORDS);
+}
 
 int pih_oracle_get_state(void* h, float* words) {
   oracle* o = (oracle*)h;
   int n = o->cfg.num_envs;
   memset(words, 0, sizeof(float) * (size_t)pih_oracle_state_words(&o->cfg) * (size_t)n);
+  if (pih_oracle_state_words(&o->cfg) > PIH_S_LATCH_Q)
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < 16; ++k) words[WIDX(PIH_S_LATCH_Q + k, i, n)] = o->use_double ? (float)o->sd[i].latch[k] : o->sf[i].latch[k];
   if (o->cfg.peg_model == PIH_PEG_PIPE)
     for (int i = 0; i < n; ++i) {
       const int D = o->use_double;
@@ -267,6 +272,9 @@ int pih_oracle_get_state(void* h, float* words) {
 int pih_oracle_set_state(void* h, const float* words) {
   oracle* o = (oracle*)h;
   int n = o->cfg.num_envs;
+  if (pih_oracle_state_words(&o->cfg) > PIH_S_LATCH_Q)
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < 16; ++k) { o->sf[i].latch[k] = words[WIDX(PIH_S_LATCH_Q + k, i, n)]; o->sd[i].latch[k] = o->sf[i].latch[k]; }
   if (o->cfg.peg_model == PIH_PEG_PIPE)
     for (int i = 0; i < n; ++i) {
       for (int k = 0; k < 3; ++k) {
@@ -434,16 +442,34 @@ int pih_oracle_grasp_labels(void* h, int W, int H, int lo, int hi, float* labels
   return 0;
 }
 
-/* PegInHole.render for envs [lo, hi): out float[hi-lo][H][W][4] = (depth, r, g, b) */
-int pih_oracle_render(void* h, int W, int H, int lo, int hi, float* out) {
-  oracle* o = (oracle*)h;
+/* PegInHole.render for envs [lo, hi): out float[hi-lo][H][W][4] = (depth, r, g, b).  latched != 0: the scene captured
+ * when the state machine entered state 2 (the reference's grasp_img, peg_in_hole.py:65-66) instead of the present one. */
+static int render_range(oracle* o, int W, int H, int lo, int hi, int latched, float* out);
+int pih_oracle_render(void* h, int W, int H, int lo, int hi, float* out) { return render_range((oracle*)h, W, H, lo, hi, 0, out); }
+int pih_oracle_render_grasp(void* h, int W, int H, int lo, int hi, float* out) { return render_range((oracle*)h, W, H, lo, hi, 1, out); }
+static int render_range(oracle* o, int W, int H, int lo, int hi, int latched, float* out) {
   for (int i = lo; i < hi; ++i) {
     float* dst = out + (size_t)(i - lo) * H * W * 4;
+    envstate_f vf = o->sf[i];
+    envstate_d vd = o->sd[i];
+    if (latched) {
+      const float* lf = o->sf[i].latch; const double* ld = o->sd[i].latch;
+      if (lf[12] != 0.0f || lf[13] != 0.0f || lf[14] != 0.0f || lf[15] != 0.0f) {
+        for (int k = 0; k < 9; ++k) vf.q[k] = lf[k];
+        for (int k = 0; k < 3; ++k) vf.ppos[k] = lf[9 + k];
+        for (int k = 0; k < 4; ++k) vf.pquat[k] = lf[12 + k];
+      }
+      if (ld[12] != 0.0 || ld[13] != 0.0 || ld[14] != 0.0 || ld[15] != 0.0) {
+        for (int k = 0; k < 9; ++k) vd.q[k] = ld[k];
+        for (int k = 0; k < 3; ++k) vd.ppos[k] = ld[9 + k];
+        for (int k = 0; k < 4; ++k) vd.pquat[k] = ld[12 + k];
+      }
+    }
     if (o->use_double) {
-      scene_d SC; build_scene_d(&o->md, &o->sd[i], &SC);
+      scene_d SC; build_scene_d(&o->md, &vd, &SC);
       for (int r = 0; r < H; ++r) for (int c = 0; c < W; ++c) render_pixel_d(&o->md, &o->cd, &SC, r, c, W, H, dst + ((size_t)r * W + c) * 4);
     } else {
-      scene_f SC; build_scene_f(&o->mf, &o->sf[i], &SC);
+      scene_f SC; build_scene_f(&o->mf, &vf, &SC);
       for (int r = 0; r < H; ++r) for (int c = 0; c < W; ++c) render_pixel_f(&o->mf, &o->cf, &SC, r, c, W, H, dst + ((size_t)r * W + c) * 4);
     }
   }

@@ -334,6 +334,7 @@ typedef struct {
   int32_t fsm_state, fsm_t;   /* scripted task */
   real rand_y, mtgt[7];
   real grasp_ang;             /* captured on entering FSM state 2 (peg_in_hole.py:65-72) */
+  real latch[16];             /* scene of the grasp image, latched at the same moment: q[9], ppos[3], pquat[4] (PIH_S_LATCH_*) */
 } FN(envstate);
 #define envstate FN(envstate)
 
@@ -1192,7 +1193,12 @@ static void FN(apply_action)(const model* M, const simcfg* C, envstate* S, const
     m3 Rp = FN(quat_to_m3)(S->pquat);
     /* on entering state 2 the reference captures the grasp image and its label rectangle; the rectangle's angle is
      * atan2(rotate_vector[1], rotate_vector[0]) with rotate_vector = R(q) [0, rand_y, 0] (peg_in_hole.py:58,65-72) */
-    if (entered && st == 2) S->grasp_ang = FN(det_atan2)(S->rand_y * Rp.m[1][1], S->rand_y * Rp.m[0][1]);
+    if (entered && st == 2) {
+      S->grasp_ang = FN(det_atan2)(S->rand_y * Rp.m[1][1], S->rand_y * Rp.m[0][1]);
+      for (int k = 0; k < 9; ++k) S->latch[k] = S->q[k];             /* self.grasp_img = self.render(), peg_in_hole.py:65-66 */
+      for (int k = 0; k < 3; ++k) S->latch[9 + k] = S->ppos[k];
+      for (int k = 0; k < 4; ++k) S->latch[12 + k] = S->pquat[k];
+    }
     v3 tp = FN(m3_v_add)(&Rp, FN(v3_make)(RC(0), S->rand_y, RC(0)), FN(v3_make)(S->ppos[0], S->ppos[1], S->ppos[2]));
     real qx = S->pquat[0], qy = S->pquat[1], qz = S->pquat[2], qw = S->pquat[3];
     real yaw = FN(det_atan2)(RC(2) * FMA(qx, qy, qw * qz), FMA(qw, qw, qx * qx) - FMA(qy, qy, qz * qz));

@@ -25,6 +25,14 @@
 #define PIH_S_RANDY 23          /* random_vector[1] ~ U(-0.03, 0.03) */
 #define PIH_S_MTGT 40           /* 40..46 arm joint position targets that persist between FSM states */
 #define PIH_S_GRASP_ANG 47      /* grasp angle captured on entering FSM state 2 (peg_in_hole.py:65-72): labels of random_grasp */
+/* scripted task, float4 slots 12..15 (words 48..63; the buffer of that task has PIH_SCRIPTED_STATE_F4 slots): the scene
+ * latched when the state machine entered state 2 - the moment the reference takes `self.grasp_img = self.render()`
+ * (peg_in_hole.py:65-66) - so that the image and the grasp labels describe the same instant: arm joints and the pose of
+ * the grasped object (peg / grasp link).  A zero quaternion = nothing captured yet. */
+#define PIH_SCRIPTED_STATE_F4 16
+#define PIH_S_LATCH_Q 48        /* 9 joint positions */
+#define PIH_S_LATCH_PPOS 57     /* 3 */
+#define PIH_S_LATCH_PQUAT 60    /* 4 */
 
 #define PIH_FLAG_DONE 1
 #define PIH_FLAG_SUCCESS 2

@@ -266,7 +266,7 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(
   float qs[nb], kpc[nb], mfc[nb];
   if (w == 0) {
     int ik_n;
-    const bool fd = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc, ik_n);
+    const bool fd = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc, ik_n, active ? e : -1);
     mailbox_put<ARM, TASK>(mb, lane, qs, kpc, mfc, fd, S);
     stat_add(P, PIH_STAT_IK_ITERS, active ? (unsigned)ik_n : 0u);
     PIH_TICK(1);
@@ -346,7 +346,7 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_rollout_
       for (int k = 0; k < A; ++k) a[k] = fmaf(u[k], 2.0f, -1.0f);
       if (!P.action_frame_env) { a[0] += off.x; a[1] += off.y; a[2] += off.z; }
       int ik_n;
-      const bool fd = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc, ik_n);
+      const bool fd = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc, ik_n, active ? e : -1);
       mailbox_put<ARM, TASK>(mb, lane, qs, kpc, mfc, fd, S);
       stat_add(P, PIH_STAT_IK_ITERS, active ? (unsigned)ik_n : 0u);
       __syncthreads();   // A: targets ready
@@ -531,7 +531,12 @@ extern "C" {
 
 int pih_abi_version(void) { return PIH_ABI_VERSION; }
 int pih_state_words(void) { return PIH_STATE_WORDS; }
-int pih_state_words_for(const pih_config* cfg) { return (cfg && cfg->peg_model == PIH_PEG_PIPE) ? 4 * PIH_PIPE_STATE_F4 : PIH_STATE_WORDS; }
+static int state_slots(const pih_config* cfg) {
+  if (cfg && cfg->peg_model == PIH_PEG_PIPE) return PIH_PIPE_STATE_F4;
+  if (cfg && cfg->task == PIH_TASK_SCRIPTED) return PIH_SCRIPTED_STATE_F4;
+  return PIH_STATE_F4;
+}
+int pih_state_words_for(const pih_config* cfg) { return 4 * state_slots(cfg); }
 int pih_action_dim(int arm) { return arm == PIH_ARM_PANDA ? 4 : (arm == PIH_ARM_UR5 ? 6 : PIH_ERR_INVALID); }
 int pih_obs_dim(void) { return 5; }
 
@@ -622,7 +627,7 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   else if (cfg->kernel_family == PIH_KERNELS_SPLIT) { h->ws = 0; h->split = 1; }
   h->no_zero_copy = cfg->host_path == 1;
   h->pipe = cfg->peg_model == PIH_PEG_PIPE;
-  k_init_state<<<(P.n + 127) / 128, 128>>>(P.state, P.n, h->pipe ? PIH_PIPE_STATE_F4 : PIH_STATE_F4);
+  k_init_state<<<(P.n + 127) / 128, 128>>>(P.state, P.n, state_slots(cfg));
   cudaError_t ce = cudaGetLastError();
   if (ce == cudaSuccess && h->pipe) ce = pih_pipe_upload_tables();
   if (ce == cudaSuccess && h->pipe) ce = cudaMalloc(&h->d_pipe_scratch, pih_pipe_scratch_bytes(P.n));
@@ -961,7 +966,14 @@ int pih_ee_pose(pih_handle* h, float* pos_dev, float* rot_dev, void* stream) {
   return PIH_OK;
 }
 
-int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, void* stream) {
+static int render_impl(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, int latched, void* stream);
+int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, void* stream) { return render_impl(h, width, height, rgbd_dev, 0, stream); }
+int pih_render_grasp(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, void* stream) {
+  if (h && h->P.task != PIH_TASK_SCRIPTED) return fail(h, PIH_ERR_INVALID, "pih_render_grasp: scripted task only", cudaSuccess);
+  return render_impl(h, width, height, rgbd_dev, 1, stream);
+}
+
+static int render_impl(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, int latched, void* stream) {
   if (!h || !rgbd_dev || width <= 0 || height <= 0) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "render() before reset()", cudaSuccess);
   USE_DEVICE(h);
@@ -969,7 +981,7 @@ int pih_render(pih_handle* h, int32_t width, int32_t height, float* rgbd_dev, vo
     cudaError_t ce = cudaMalloc(&h->d_scene, (size_t)h->P.n * PIH_SCENE_WORDS * sizeof(float));
     if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "scene allocation", ce);
   }
-  LAUNCH_ARM(k_scene, h, stream, h->P, h->d_scene, (int)width, (int)height);
+  LAUNCH_ARM(k_scene, h, stream, h->P, h->d_scene, (int)width, (int)height, latched);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_scene launch", ce);
   dim3 grid((unsigned)((width * height + 256 * PIH_RENDER_PPT - 1) / (256 * PIH_RENDER_PPT)), (unsigned)h->P.n);

@@ -667,7 +667,7 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32, 1) k_pipe_arm
   fk<ARM, nb>(S.q, F);
   float qs[nb], kpc[nb], mfc[nb];
   int ik_n;
-  const bool fsm_done = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc, ik_n);
+  const bool fsm_done = apply_action<ARM, TASK>(P, S, F, a, off, qs, kpc, mfc, ik_n, e);
   float tau[nb];
 #pragma unroll
   for (int i = 0; i < nb; ++i) tau[i] = -(T.damp[i] * S.qd[i]);
@@ -776,7 +776,7 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_reset(
   S.episode += 1;
   reset_env_pipe<ARM, TASK>(P, S, B, sm, lane, qj, qdj, (unsigned)(P.env_id_base + e));
   __syncwarp();
-  for (int k = lane; k < 4 * PIH_PIPE_STATE_F4; k += 32) w[k] = 0.0f;
+  for (int k = lane; k < 4 * PIH_PIPE_STATE_F4; k += 32) if (k < PIH_S_LATCH_Q || k >= PIH_PS_BASE) w[k] = 0.0f;   // (the latched grasp scene stays)
   __syncwarp();
   envstate_to_words(w, S);
   pipe_to_words(w, lane, B, qj, qdj);
@@ -1243,7 +1243,7 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_step(S
     observe<ARM>(S, off, o);
     // ---- store: pack the words in shared memory, lane l writes slot l
     __syncwarp();
-    for (int k = lane; k < 4 * PIH_PIPE_STATE_F4; k += 32) w[k] = 0.0f;
+    for (int k = lane; k < 4 * PIH_PIPE_STATE_F4; k += 32) if (k < PIH_S_LATCH_Q || k >= PIH_PS_BASE) w[k] = 0.0f;   // (the latched grasp scene stays)
     __syncwarp();
     envstate_to_words(w, S);
     pipe_to_words(w, lane, B, qj, qdj);

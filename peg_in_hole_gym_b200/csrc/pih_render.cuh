@@ -79,13 +79,31 @@ PIH_D float4 shade_pixel(int obj, float best, v3 nb) {
 
 // scene block per env: eye(3) Rfb(9) pfb(3) Rbox0(9) cbox0(3) Rbox1(9) cbox1(3) | 39: screen rects (r0,r1,c0,c1) of the
 // free body, the hole and the two finger boxes
-template <int ARM> __global__ void __launch_bounds__(128) k_scene(SimParams P, float* __restrict__ scene, int W, int H) {
+// latched != 0 (scripted task): the scene captured when the state machine entered state 2 (state slots 12..15) instead of
+// the current one - the reference's `grasp_img` (peg_in_hole.py:65-66); envs that have not captured yet show the present
+template <int ARM> __global__ void __launch_bounds__(128) k_scene(SimParams P, float* __restrict__ scene, int W, int H, int latched) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.n) return;
   constexpr int nb = ArmDims<ARM>::NB;
   const ArmTables& T = c_arm[ARM];
   EnvState S;
   load_state(P, e, S);
+  if (latched) {
+    float w[16];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const float4 v = __ldg(&P.state[(size_t)(12 + s) * P.n + e]);
+      w[4 * s] = v.x; w[4 * s + 1] = v.y; w[4 * s + 2] = v.z; w[4 * s + 3] = v.w;
+    }
+    if (w[12] != 0.0f || w[13] != 0.0f || w[14] != 0.0f || w[15] != 0.0f) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) S.q[k] = w[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) S.ppos[k] = w[9 + k];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) S.pquat[k] = w[12 + k];
+    }
+  }
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
   v3 eye; m3 Ree;

@@ -381,8 +381,22 @@ template <int ARM> PIH_D void observe(const EnvState& S, v3 off, float (&obs)[5]
 // apply_action: panda_execute / ur_execute (envs/utils.py:60-82) -> joint position targets, gains and force caps.
 // Scripted task: apply_action is `pass` (peg_in_hole.py:30-31); the command comes from the grasp state machine
 // (peg_in_hole.py:39-212).  Returns true when the FSM has reached its final state.
+// the scene of the scripted task's grasp image (PIH_S_LATCH_*): written straight to the env's state slots 12..15
+PIH_D void latch_scene(const SimParams& P, int e, const EnvState& S) {
+  float w[16];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w[k] = S.q[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) w[9 + k] = S.ppos[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) w[12 + k] = S.pquat[k];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) P.state[(size_t)(12 + s) * P.n + e] = make_float4(w[4 * s], w[4 * s + 1], w[4 * s + 2], w[4 * s + 3]);
+}
+
+// latch_env: env index whose grasp scene may be latched by this call (-1: none - parity hooks, frozen or padding lanes)
 template <int ARM, int TASK> PIH_D bool apply_action(const SimParams& P, EnvState& S, const FK<ARM>& F, const float* action, v3 off, float* qstar,
-                                           float* kpc, float* mfc, int& ik_n) {
+                                           float* kpc, float* mfc, int& ik_n, int latch_env = -1) {
   ik_n = 0;
   constexpr int nb = ArmDims<ARM>::NB, na = ArmDims<ARM>::NARM;
   const ArmTables& T = c_arm[ARM];
@@ -408,7 +422,10 @@ template <int ARM, int TASK> PIH_D bool apply_action(const SimParams& P, EnvStat
     m3 Rp = quat_to_m3(S.pquat);
     // entering state 2 the reference renders the grasp image and labels it with the rectangle whose angle is
     // atan2 of R(q_peg) random_vector = rand_y * (second column of R) (peg_in_hole.py:58,65-72)
-    if (entered && st == 2) S.grasp_ang = det_atan2(S.rand_y * Rp.m[1][1], S.rand_y * Rp.m[0][1]);
+    if (entered && st == 2) {
+      S.grasp_ang = det_atan2(S.rand_y * Rp.m[1][1], S.rand_y * Rp.m[0][1]);
+      if (latch_env >= 0) latch_scene(P, latch_env, S);       // self.grasp_img = self.render() (peg_in_hole.py:65-66)
+    }
     v3 tp = mv_add(Rp, mk(0.0f, S.rand_y, 0.0f), mk(S.ppos[0], S.ppos[1], S.ppos[2]));
     float qx = S.pquat[0], qy = S.pquat[1], qz = S.pquat[2], qw = S.pquat[3];
     float yaw = det_atan2(2.0f * fmaf(qx, qy, qw * qz), fmaf(qw, qw, qx * qx) - fmaf(qy, qy, qz * qz));
@@ -504,13 +521,14 @@ __device__ __forceinline__ void step_back_ws(const SimParams& P, EnvState& S, co
 // One env.step for one env.  Returns false if the env was frozen (done and not reset): outputs untouched.
 template <int ARM, int TASK> __device__ __noinline__ bool step_env(const SimParams& P, EnvState& S, const float* action, v3 off, unsigned gid,
                                                               float (&obs)[5], float& reward, unsigned char& done) {
+  const int latch_env = (int)(gid - (unsigned)P.env_id_base);   // local env index
   if (S.flags & PIH_FLAG_DONE) return false;
   constexpr int nb = ArmDims<ARM>::NB;
   FK<ARM> F;
   fk<ARM, nb>(S.q, F);
   float qstar[nb], kpc[nb], mfc[nb];
   int ik_n;
-  const bool fsm_done = apply_action<ARM, TASK>(P, S, F, action, off, qstar, kpc, mfc, ik_n);
+  const bool fsm_done = apply_action<ARM, TASK>(P, S, F, action, off, qstar, kpc, mfc, ik_n, latch_env);
   stat_add(P, PIH_STAT_IK_ITERS, (unsigned)ik_n);
   step_back<ARM, TASK>(P, S, F, qstar, kpc, mfc, fsm_done, true, off, gid, obs, reward, done);
   return true;

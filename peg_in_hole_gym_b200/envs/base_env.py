@@ -8,7 +8,7 @@ import torch
 
 from .. import gym_shim as gym
 from ..sim import BatchedSim
-from .peg_in_hole import PegInHole, PegInHoleScripted, PegInHoleUR5
+from .peg_in_hole import PegInHole, PegInHolePipe, PegInHoleScripted, PegInHoleScriptedPipe, PegInHoleUR5
 from .random_fly import RandomFly
 from .utils import MultiAgentActionSpace, MultiAgentObservationSpace, test_mode
 
@@ -16,6 +16,8 @@ TASK_LIST = {
     'peg-in-hole': PegInHole,      # base_env.py:9-11
     'peg-in-hole-ur5': PegInHoleUR5,
     'peg-in-hole-scripted': PegInHoleScripted,   # the scripted grasp FSM the reference ships (peg_in_hole.py:39-225)
+    'peg-in-hole-pipe': PegInHolePipe,           # action-driven, the reference's 25-link pipe.urdf as the peg
+    'peg-in-hole-scripted-pipe': PegInHoleScriptedPipe,   # the shipped task on the shipped object
     'random-fly': RandomFly,       # README.md:38 (source missing from the snapshot; NEW semantics)
 }
 
@@ -67,7 +69,7 @@ class BaseEnv(gym.Env):
 
     def __init__(self, client, task='peg-in-hole', task_num=1, offset=[0, 0, 0], args=None, is_test=False, *,
                  arm=None, seed=0, max_steps=0, auto_reset=False, action_frame='world', solver_iters=50, ik_iters=20,
-                 device=None, as_lists=False, _mp_num=1, _env_id_base=0):
+                 device=None, as_lists=False, peg_model=None, _mp_num=1, _env_id_base=0):
         assert task in TASK_LIST, "Please regisiter your custom env first!"
         assert (task_num == 1 or (task_num > 1 and list(offset) != [0, 0, 0])), "Offset is in valid."
         self.task, self.task_num, self.offset, self.args = task, task_num, offset, args
@@ -78,6 +80,8 @@ class BaseEnv(gym.Env):
         self.plugin = self.sub_env(None, offset, args)
         if arm is not None:
             self.plugin.arm = arm
+        if peg_model is not None:
+            self.plugin.peg_model = peg_model
         cfg = dict(task=self.plugin.native_task, arm=self.plugin.arm, dt=1.0 / 240.0)
         cfg.update(self.plugin.sim_config())
         cfg["arm"] = self.plugin.arm

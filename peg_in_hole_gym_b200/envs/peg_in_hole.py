@@ -16,6 +16,7 @@ class PegInHole(MetaEnv):
     observation_space = spaces.Box(np.array([-1] * 5), np.array([1] * 5))
     native_task = "peg-in-hole"
     arm = "panda"
+    peg_model = "rigid"      # 'rigid': one end segment of pipe.urdf; 'pipe': the whole 25-link chain (peg_in_hole.py:240-245)
 
     def __init__(self, client, offset=[0, 0, 0], args=None):
         self.pandaUid = 0
@@ -24,7 +25,13 @@ class PegInHole(MetaEnv):
         super().__init__(client, offset, args)
 
     def sim_config(self):
-        return dict(task="peg-in-hole", arm=self.arm, dt=1.0 / 240.0)  # timeStep peg_in_hole.py:254
+        return dict(task="peg-in-hole", arm=self.arm, dt=1.0 / 240.0, peg_model=self.peg_model)  # timeStep peg_in_hole.py:254
+
+
+class PegInHolePipe(PegInHole):
+    """The action-driven task on the object the reference loads: pipe.urdf, 25 links / 23 continuous joints with random
+    bends, grasp link 0 or 23, success on that link (peg_in_hole.py:239-245,266,114-117).  Warp-per-env kernels."""
+    peg_model = "pipe"
 
 
 class PegInHoleUR5(PegInHole):
@@ -39,13 +46,18 @@ class PegInHoleScripted(PegInHole):
     steps of 1/240 s) and returns the success reward of peg_in_hole.py:114-117.  The state machine runs inside the
     rollout kernel; the observation is the 5-vector; the camera image and the grasp label images of peg_in_hole.py:66-98
     come from ``render()`` and ``random_grasp_labels()``.
-    Differences flagged NEW: rigid peg segment instead of the 25-link pipe; the JOINT_GEAR grasp constraint
-    (peg_in_hole.py:99-104) is replaced by the friction grasp alone."""
+    The grasp constraint of peg_in_hole.py:99-104 is built as its evident intent (grasp point pinned to the end effector
+    while the state is 4..6; csrc/pih_constants.h PIH_PAIR_GRASP).  `PegInHoleScriptedPipe` runs it on the 25-link pipe."""
     native_task = "peg-in-hole-scripted"
     EPISODE_STEPS = 2226
 
     def sim_config(self):
-        return dict(task="peg-in-hole-scripted", arm="panda", dt=1.0 / 240.0)
+        return dict(task="peg-in-hole-scripted", arm="panda", dt=1.0 / 240.0, peg_model=self.peg_model)
+
+    def render(self, mode="rgb_array", width=300, height=300):
+        """The observation of the shipped task: ``grasp_img``, the camera image taken when the state machine entered
+        state 2 (peg_in_hole.py:33-37,65-66) - the scene the grasp labels describe, not the scene at episode end."""
+        return self.p.render_grasp(width, height)
 
     def apply_action(self, action):      # peg_in_hole.py:30-31
         return action
@@ -53,8 +65,16 @@ class PegInHoleScripted(PegInHole):
     def native_step(self, action):       # get_info -> random_grasp(): `while not done` loop (peg_in_hole.py:52-112)
         self.p.rollout(self.EPISODE_STEPS, count=False)
 
+    def grasp_image(self, width=300, height=300):
+        return self.p.render_grasp(width, height)
+
     def random_grasp_labels(self, width=300, height=300):
         """What the reference's ``random_grasp`` returns beside the reward (peg_in_hole.py:119):
         ``[[pos_img, sin_img, cos_img, wid_img], [x, y, angle_deg, width, length]]`` for every env, as tensors
         ``labels[N, 4, H, W]`` and ``params[N, 5]`` (the rectangle was captured when the state machine entered state 2)."""
         return self.p.grasp_labels(width, height)
+
+
+class PegInHoleScriptedPipe(PegInHoleScripted):
+    """The shipped task on the shipped object: scripted grasp -> insert episode with the 25-link pipe."""
+    peg_model = "pipe"

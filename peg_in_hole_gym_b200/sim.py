@@ -185,6 +185,14 @@ class BatchedSim:
         N.check(self._L.pih_render(self._h, int(width), int(height), out.data_ptr(), self._stream()), self._h, "pih_render")
         return out
 
+    def render_grasp(self, width=300, height=300, out=None):
+        """Scripted task: the camera on the scene latched when the state machine entered state 2 - the reference's
+        ``grasp_img`` (peg_in_hole.py:65-66), the image its grasp labels belong to."""
+        if out is None:
+            out = torch.empty(self.n, height, width, 4, dtype=torch.float32, device=self.device)
+        N.check(self._L.pih_render_grasp(self._h, int(width), int(height), out.data_ptr(), self._stream()), self._h, "pih_render_grasp")
+        return out
+
     def grasp_labels(self, width=300, height=300):
         """Label images of the shipped task's random_grasp (peg_in_hole.py:41-45,65-98): ``(labels[N, 4, H, W], params[N, 5])``
         = ([pos_img, sin_img, cos_img, wid_img], [x, y, angle in degrees, width, length])."""

@@ -139,6 +139,13 @@ class Oracle:
         lib().pih_oracle_render(self.h, width, height, lo, hi, _p(img))
         return img
 
+    def render_grasp(self, width=300, height=300, lo=0, hi=None):
+        hi = self.n if hi is None else hi
+        img = np.zeros((hi - lo, height, width, 4), np.float32)
+        lib().pih_oracle_render_grasp.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        lib().pih_oracle_render_grasp(self.h, width, height, lo, hi, _p(img))
+        return img
+
     def grasp_labels(self, width=300, height=300, lo=0, hi=None):
         hi = self.n if hi is None else hi
         lab = np.zeros((hi - lo, 4, height, width), np.float32)

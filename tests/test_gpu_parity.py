@@ -499,6 +499,36 @@ def test_camera_render_matches_oracle_and_full_size():
     env.close()
 
 
+def test_grasp_image_is_the_scene_latched_on_entering_state_2():
+    """the reference returns `grasp_img`, rendered when the state machine enters state 2, together with the
+    grasp labels (peg_in_hole.py:33-37,65-66).  The scene is latched into the state at that step; pih_render_grasp casts it.
+    CUDA == oracle exactly; the image taken at the end of the episode (arm parked) is a different one."""
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    n = 6
+    sim = BatchedSim(n, task="peg-in-hole-scripted", offset=(2.0, 3.0, 0.0), seed=3, device=0)
+    orc = ol.Oracle(ol.make_config(n, task=2, offset=(2.0, 3.0, 0.0), seed=3))
+    sim.reset(); orc.reset()
+    sim.rollout(300); orc.rollout(300)                        # state 1: nothing captured yet -> the present scene
+    assert np.array_equal(sim.render_grasp(80, 64).cpu().numpy(), sim.render(80, 64).cpu().numpy())
+    sim.rollout(241); orc.rollout(241)                        # step 541 = first step of state 2 (59 + 481 + 1)
+    at_capture = sim.render(80, 64).cpu().numpy()             # scene before that step's physics = what was latched ...
+    _assert_state_equal(sim, orc)
+    sim.rollout(1685); orc.rollout(1685)                      # ... to the end of the episode
+    _assert_state_equal(sim, orc)
+    g, c = sim.render_grasp(80, 64).cpu().numpy(), orc.render_grasp(80, 64)
+    assert np.array_equal(g, c)
+    assert not np.array_equal(g, sim.render(80, 64).cpu().numpy()), "the latched image must not be the end-of-episode scene"
+    # the latch holds the pre-step scene of step 541; one engine step later the rendered scene has barely moved
+    assert np.abs(g[..., 0] - at_capture[..., 0]).mean() < 5e-3
+    import peg_in_hole_gym_b200 as gym
+    env = gym.make('peg-in-hole-mp-v0', client=gym.DIRECT, task='peg-in-hole-scripted', mp_num=1, sub_num=n, offset=[2., 3., 0.], seed=3, shard=False)
+    env.reset()
+    env.step(env.action_space.sample_array())
+    img = env.render('rgb_array', 80, 64)
+    assert np.array_equal(img.cpu().numpy().reshape(n, 64, 80, 4), g)
+    env.close()
+
+
 @pytest.mark.parametrize("arm,task,fly", [("panda", "peg-in-hole", "banana"), ("ur5", "peg-in-hole", "banana"),
                                           ("panda", "random-fly", "amicelli")])
 def test_randomised_states_fuzz_bit_exact(arm, task, fly):
