@@ -278,6 +278,9 @@ def main():
                     help="every step all ranks deliver their (obs,reward,done) rows to rank 0: 'nccl' = pack + gather collective; "
                          "'peer' = the step kernel stores them into rank 0's buffer over NVLink peer memory and signals a flag "
                          "(default with more than one GPU); 'none' = independent ranks")
+    ap.add_argument("--peer-wait", choices=["folded", "kernel"], default="folded",
+                    help="gather 'peer': rank 0 waits for the previous step's rows inside its next step kernel (folded) or "
+                         "with a wait kernel after every step (kernel)")
     ap.add_argument("--l2", choices=["rotate", "flush"], default="rotate",
                     help="rotate: inputs larger than L2 (many independent batches round-robin); flush: one batch, L2 flushed between steps")
     ap.add_argument("--no-cpu", action="store_true")
@@ -367,7 +370,9 @@ def main():
         if peer is not None:
             # outputs go straight into rank 0's learner buffer, then the flag; rank 0's kernel first waits for the
             # previous step's rows of every rank (the consumer's wait, folded into its next launch)
-            peer.step(a, sm, wait_prev=(rank == 0))
+            peer.step(a, sm, wait_prev=(rank == 0 and args.peer_wait == "folded"))
+            if rank == 0 and args.peer_wait == "kernel":
+                peer.wait()
         else:
             sm.step(a)
             if gather == "nccl":
@@ -515,7 +520,7 @@ def main():
                               f"batch b pre-rolled to episode phase b*{MAX_STEPS}/{nb_batches} and visited with stride {stride} (coprime), so every window of "
                               "consecutive steps covers the phases evenly; K launches inside one CUDA-event pair"
                               if args.l2 == "rotate" else "flushed between timed steps (256 MiB memset); per-step CUDA events summed"),
-                       "gather_to_rank0": gather if world > 1 else False,
+                       "gather_to_rank0": gather if world > 1 else False, "peer_wait": args.peer_wait if gather == "peer" else None,
                        "parallelism": f"env-sharded x{world}, " + ("no data-path collective" if gather == "none" else
                                                                     ("rows stored into rank 0's learner buffer by the step kernel over NVLink peer memory (no collective)"
                                                                      if gather == "peer" else "pack + NCCL gather to rank 0 every step"))},

@@ -47,6 +47,26 @@ template <int ARM> PIH_D void frozen_outputs(const EnvState& S, v3 off, float (&
   d = 1;
 }
 
+// A warp's 32 observation rows are 640 contiguous bytes: transposed through shared memory so that the warp writes five
+// full 128-byte lines instead of 160 scattered words (what counts when obs is peer memory over NVLink or mapped host
+// memory).  A partial warp (tail of the batch) stores its rows directly.
+PIH_D void store_obs_rows(float* __restrict__ obs, int e, const float (&o)[5], float* so_block) {
+  const unsigned m = __activemask();
+  const int lane = threadIdx.x & 31;
+  if (m != 0xffffffffu) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) obs[5 * (size_t)e + k] = o[k];
+    return;
+  }
+  float* so = so_block + 160 * (threadIdx.x >> 5);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) so[5 * lane + k] = o[k];
+  __syncwarp();
+  float* dst = obs + 5 * (size_t)(e - lane);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) dst[32 * k + lane] = so[32 * k + lane];
+}
+
 template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOCKS) k_step(SimParams P, const float* __restrict__ action, float* __restrict__ obs,
                                                                 float* __restrict__ reward, unsigned char* __restrict__ done) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,10 +80,9 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOC
   unsigned char d;
   if (step_env<ARM, TASK>(P, S, a, env_offset(P, e), (unsigned)(P.env_id_base + e), o, r, d)) store_state(P, e, S);
   else frozen_outputs<ARM>(S, env_offset(P, e), o, r, d);
-  if (obs) {
-#pragma unroll
-    for (int k = 0; k < 5; ++k) obs[5 * (size_t)e + k] = o[k];
-  }
+  __shared__ float so_block[4 * 160];
+  __syncwarp(__activemask());   // (stepped and frozen lanes meet again here)
+  if (obs) store_obs_rows(obs, e, o, so_block);
   if (reward) reward[e] = r;
   if (done) done[e] = d;
 }
@@ -135,10 +154,9 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOC
     unsigned ws = __reduce_add_sync(m, nsteps), wd = __reduce_add_sync(m, ndone);
     if ((threadIdx.x & 31) == (unsigned)(__ffs(m) - 1) && ws) { atomicAdd(&counters[0], (unsigned long long)ws); atomicAdd(&counters[1], (unsigned long long)wd); }
   }
-  if (obs) {
-#pragma unroll
-    for (int k = 0; k < 5; ++k) obs[5 * (size_t)e + k] = o[k];
-  }
+  __shared__ float so_block[4 * 160];
+  __syncwarp(__activemask());
+  if (obs) store_obs_rows(obs, e, o, so_block);
   if (reward) reward[e] = r;
   if (done) done[e] = d;
 }

@@ -13,8 +13,12 @@
 //                Lane i owns dof i: its unconstrained velocity, its column of M^-1 (its own unit-impulse response, 29
 //                registers), its motor row.  Lane s owns collision segment s (25 cylinders).  Serial recurrences over the
 //                chain (FK, the articulated-inertia pass) are run by all lanes redundantly from shared memory; sums over
-//                degrees of freedom are xor-butterflies (fixed order, restated by the oracle: FN(bfly32)).  Constraint
-//                rows (Jacobian + M^-1 J^T per row, 256 B) live in shared memory, 28 KB per env.
+//                degrees of freedom are xor-butterflies (fixed order, restated by the oracle: FN(bfly32)).  The step is
+//                the latency of one warp's dependent instruction stream, so what matters is how many warps an SM holds:
+//                body loops are rolled (one z-joint and one x-joint body per pass, small code), M^-1 lives in shared
+//                memory (3.6 KB), and the constraint rows (Jacobian + M^-1 J^T, 384 B each, read once per solver sweep)
+//                live in a per-env global scratch block that stays in L1/L2 - 13 KB of shared memory and <= 128
+//                registers per warp-env, 16 resident envs per SM.
 // Bit-comparable with oracle/pih_pipe_impl.h (float build): same chains of explicit FMAs, file compiled with -fmad=false.
 #pragma once
 #include "pih_step.cuh"
@@ -42,6 +46,14 @@ namespace pih {
 #define PA_IK_N 228         // statistics: IK iterations of this step
 
 constexpr int PNB = PIH_PIPE_NBODY, PND = PIH_PIPE_NDOF, PNSEG = PIH_PIPE_NSEG;
+// resident warp-envs per SM the step kernel is compiled for (register budget 65536 / (32 * this))
+#ifndef PIH_PIPE_MIN_BLOCKS
+#define PIH_PIPE_MIN_BLOCKS 16
+#endif
+// warp-envs per CTA of the step kernel
+#ifndef PIH_PIPE_WARPS
+#define PIH_PIPE_WARPS 1
+#endif
 
 // ---- shared-memory layout of k_pipe_step (floats)
 constexpr int SM_SW = 0;                                  // state words [128]
@@ -58,12 +70,15 @@ constexpr int SM_DINV = SM_UD + PNB * 6;                  // [24]
 constexpr int SM_UU = SM_DINV + PNB;                      // u [24]
 constexpr int SM_CON = SM_UU + PNB;                       // contacts [PIH_PIPE_MAXC][12]: p, n, dist, mu, pair, seg, arm_body, arm slot
 constexpr int SM_ROWS = SM_CON + PIH_PIPE_MAXC * 12;      // row scalars [3 * MAXC][4]: dinv, diag, b, lam
-constexpr int SM_J = SM_ROWS + 3 * PIH_PIPE_MAXC * 4;     // pipe Jacobian rows [3 * MAXC][32]
-constexpr int SM_MJ = SM_J + 3 * PIH_PIPE_MAXC * 32;      // M^-1 J^T rows [3 * MAXC][32]
-constexpr int SM_JA = SM_MJ + 3 * PIH_PIPE_MAXC * 32;     // arm parts [3 * ARMROWS][16] (9 used)
-constexpr int SM_MJA = SM_JA + 3 * PIH_PIPE_ARMROWS * 16;
-constexpr int SM_TOTAL = SM_MJA + 3 * PIH_PIPE_ARMROWS * 16;
+constexpr int SM_MCOL = SM_ROWS + 3 * PIH_PIPE_MAXC * 4;  // M^-1 of the chain: [c][lane] = velocity change of dof c for a unit impulse on dof `lane`
+constexpr int SM_JTMP = SM_MCOL + PND * 32;               // the Jacobian row being built [32] (+ arm part [16])
+constexpr int SM_TOTAL = SM_JTMP + 48;
+constexpr int SM_UH = SM_CON;                             // unit-impulse pass: uh[b][lane] (dead before the contacts are written)
+static_assert(PNB * 32 <= PIH_PIPE_MAXC * 12 + 3 * PIH_PIPE_MAXC * 4, "uh aliases the contact + row-scalar region");
 constexpr int kPipeSmemBytes = SM_TOTAL * 4;
+// constraint rows in the per-env global scratch block: [row][96] floats = J[32] | M^-1 J^T[32] | arm J[16] | arm M^-1 J^T[16]
+constexpr int kRowWords = 96;
+constexpr int kRowBufWords = 3 * PIH_PIPE_MAXC * kRowWords;
 
 __host__ __device__ constexpr int pipe_axis(int b) { return (b & 1) ? 2 : 0; }
 PIH_D float pipe_len(int b) { return (b == 1) ? (float)(PIH_PIPE_LINK1_Y + PIH_PIPE_PITCH) : (float)PIH_PIPE_PITCH; }
@@ -179,6 +194,25 @@ PIH_D void ldl6_solve(const Ldl6& F, const float* rhs, float* x) {
 // pipe block of the state as the warp sees it (every lane holds the base; joint b lives on lane 5 + b)
 struct PipeBase { float pos[3], quat[4], vel[3], ang[3]; int grasp_idx; };
 
+// Chain passes are ROLLED: bodies alternate z joints (odd b) and x joints (even b), so a pass is a loop over the pairs
+// (b, b + 1) with one instantiation of the body per axis - twenty times less code than the unrolled chain, which is what a
+// lone warp per scheduler needs (instruction fetch was 37 % of the stall samples of the unrolled kernel).
+template <class F> PIH_D void chain_forward(F&& body) {      // b = 1 .. 23
+#pragma unroll 1
+  for (int b = 1; b < PNB; b += 2) {
+    body(std::integral_constant<int, 2>{}, b);
+    if (b + 1 < PNB) body(std::integral_constant<int, 0>{}, b + 1);
+  }
+}
+template <class F> PIH_D void chain_backward(F&& body) {     // b = 23 .. 1
+#pragma unroll 1
+  for (int b = PNB - 1; b >= 1; b -= 2) {
+    body(std::integral_constant<int, 2>{}, b);
+    if (b - 1 >= 1) body(std::integral_constant<int, 0>{}, b - 1);
+  }
+}
+static_assert((PNB - 1) % 2 == 1, "the last body of the chain hangs on a z joint");
+
 // FK of the chain into shared memory: Rw[b], pw[b], sn[b], cs[b].  All lanes run the recurrence (identical values).
 PIH_D void pipe_fk(float* sm, const PipeBase& B, int lane, float qj_lane) {
   {
@@ -194,15 +228,15 @@ PIH_D void pipe_fk(float* sm, const PipeBase& B, int lane, float qj_lane) {
 #pragma unroll
   for (int i = 0; i < 9; ++i) sm[SM_RW + i] = R.m[i / 3][i % 3];
   sts3(&sm[SM_PW], p);
-  sfor<1, PNB>([&](auto b_) {
-    constexpr int b = decltype(b_)::value;
+  chain_forward([&](auto ax_, int b) {
+    constexpr int ax = decltype(ax_)::value;
     const float L = pipe_len(b);
     p = mk(fmaf(L, R.m[0][1], p.x), fmaf(L, R.m[1][1], p.y), fmaf(L, R.m[2][1], p.z));
     const float s = sm[SM_SN + b], c = sm[SM_CS + b];
     m3 N;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      if (pipe_axis(b) == 2) {
+      if (ax == 2) {
         N.m[i][0] = fmaf(s, R.m[i][1], c * R.m[i][0]);
         N.m[i][1] = fmaf(c, R.m[i][1], -(s * R.m[i][0]));
         N.m[i][2] = R.m[i][2];
@@ -244,12 +278,12 @@ PIH_D m3 pipe_Rl(int axis, float s, float c) {
   return R;
 }
 
-// ABA of the floating chain (oracle: pipe_dynamics).  Serial passes by all lanes; results: lane i gets vstar of dof i and
-// its column col[0..28] of M^-1 (velocity change of every dof for a unit impulse on dof i); the base factorisation and the
-// per-body U, U/D, 1/D, u stay in shared memory for the unit-impulse pass.
-PIH_D void pipe_dynamics(float* sm, const PipeBase& B, int lane, float qdj_lane, float dt, float g, float& vstar_lane, float (&col)[PND]) {
+// ABA of the floating chain (oracle: pipe_dynamics).  Serial passes by all lanes (rolled); results: lane i gets vstar of
+// dof i, and shared memory gets M^-1: SM_MCOL[c][i] = velocity change of dof c for a unit impulse on dof i (lane i's own
+// response pass).  The per-body U, U/D, 1/D, u stay in shared memory.
+PIH_D void pipe_dynamics(float* sm, const PipeBase& B, int lane, float qdj_lane, float dt, float g, float& vstar_lane) {
   const PipeModel PM = pipe_model();
-  // joint rates to shared memory (reuse SM_UU until the inward pass overwrites it)
+  // joint rates to shared memory (SM_UU until the inward pass overwrites it with u)
   {
     const int b = lane - 5;
     if (b >= 1 && b < PNB) sm[SM_UU + b] = qdj_lane;
@@ -271,9 +305,8 @@ PIH_D void pipe_dynamics(float* sm, const PipeBase& B, int lane, float qdj_lane,
     pA0.a = vadd(vcross(w, La), vcross(v, Ll));
     pA0.l = vcross(w, Ll);
   }
-  sfor<1, PNB>([&](auto b_) {
-    constexpr int b = decltype(b_)::value;
-    constexpr int ax = pipe_axis(b);
+  chain_forward([&](auto ax_, int b) {
+    constexpr int ax = decltype(ax_)::value;
     sv vp = pipe_motion_to_child<ax>(sm[SM_SN + b], sm[SM_CS + b], pipe_len(b), vel);
     const float w = sm[SM_UU + b];
     sv cb;
@@ -288,14 +321,18 @@ PIH_D void pipe_dynamics(float* sm, const PipeBase& B, int lane, float qdj_lane,
     sts3(&sm[SM_CB + 6 * b], cb.a); sts3(&sm[SM_CB + 6 * b + 3], cb.l);
     sts3(&sm[SM_PB + 6 * b], pa); sts3(&sm[SM_PB + 6 * b + 3], pl);
   });
-  // (C) inward pass.  The running articulated inertia / bias of the CHILD side is carried in registers: body b's own
-  //     rigid inertia plus what its child handed up.
+  // (C) inward pass.  The articulated inertia / bias handed up by the child is carried in registers; body 23 (the tip)
+  //     has none: `have` stays false for it.
   m3 accA, accB, accC;
   sv accp;
+  accp.a = mk(0.0f, 0.0f, 0.0f); accp.l = accp.a;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { accA.m[r][c] = 0.0f; accB.m[r][c] = 0.0f; accC.m[r][c] = 0.0f; }
   bool have = false;
-  sfor<1, PNB>([&](auto k_) {
-    constexpr int b = PNB - decltype(k_)::value;     // 23 .. 1
-    constexpr int ax = pipe_axis(b);
+  chain_backward([&](auto ax_, int b) {
+    constexpr int ax = decltype(ax_)::value;
     m3 IA, IB, IC;
     sv pAb;
 #pragma unroll
@@ -400,9 +437,8 @@ PIH_D void pipe_dynamics(float* sm, const PipeBase& B, int lane, float qdj_lane,
     for (int k = 0; k < 6; ++k) vstar_lane = (lane == k) ? vsb[k] : vstar_lane;
     sv acc;
     acc.a = mk(a0[0], a0[1], a0[2]); acc.l = mk(a0[3], a0[4], a0[5]);
-    sfor<1, PNB>([&](auto b_) {
-      constexpr int b = decltype(b_)::value;
-      constexpr int ax = pipe_axis(b);
+    chain_forward([&](auto ax_, int b) {
+      constexpr int ax = decltype(ax_)::value;
       sv a = pipe_motion_to_child<ax>(sm[SM_SN + b], sm[SM_CS + b], pipe_len(b), acc);
       a.a = vadd(a.a, lds3(&sm[SM_CB + 6 * b]));
       a.l = vadd(a.l, lds3(&sm[SM_CB + 6 * b + 3]));
@@ -414,19 +450,18 @@ PIH_D void pipe_dynamics(float* sm, const PipeBase& B, int lane, float qdj_lane,
       vstar_lane = (lane == 5 + b) ? vsj : vstar_lane;
     });
   }
-  // (F) unit-impulse response of dof `lane` (lanes 29..31: no impulse, all zeros)
+  // (F) unit-impulse response of dof `lane` (lanes 29..31: no impulse, all zeros) -> column `lane` of SM_MCOL
   {
     sv ph;
     ph.a = mk(0.0f, 0.0f, 0.0f); ph.l = ph.a;
-    float uh[PNB];
-    sfor<1, PNB>([&](auto k_) {
-      constexpr int b = PNB - decltype(k_)::value;
-      constexpr int ax = pipe_axis(b);
+    chain_backward([&](auto ax_, int b) {
+      constexpr int ax = decltype(ax_)::value;
       const float sp = vget<ax>(ph.a);
-      uh[b] = ((5 + b == lane) ? 1.0f : 0.0f) - sp;
+      const float uh = ((5 + b == lane) ? 1.0f : 0.0f) - sp;
+      sm[SM_UH + 32 * b + lane] = uh;
       sv pa;
-      pa.a = vaxpy(uh[b], lds3(&sm[SM_UD + 6 * b]), ph.a);
-      pa.l = vaxpy(uh[b], lds3(&sm[SM_UD + 6 * b + 3]), ph.l);
+      pa.a = vaxpy(uh, lds3(&sm[SM_UD + 6 * b]), ph.a);
+      pa.l = vaxpy(uh, lds3(&sm[SM_UD + 6 * b + 3]), ph.l);
       // the oracle adds the transformed force to the parent's (zero) accumulator: 0 + x keeps x bit for bit
       sv fp = pipe_force_to_parent<ax>(sm[SM_SN + b], sm[SM_CS + b], pipe_len(b), pa);
       ph.a = vadd(mk(0.0f, 0.0f, 0.0f), fp.a);
@@ -437,20 +472,20 @@ PIH_D void pipe_dynamics(float* sm, const PipeBase& B, int lane, float qdj_lane,
     for (int j = 0; j < 6; ++j) r6[j] = ((j == lane) ? 1.0f : 0.0f) - r6[j];
     ldl6_solve(Fz, r6, x6);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) col[j] = x6[j];
+    for (int j = 0; j < 6; ++j) sm[SM_MCOL + 32 * j + lane] = x6[j];
     sv acc;
     acc.a = mk(x6[0], x6[1], x6[2]); acc.l = mk(x6[3], x6[4], x6[5]);
-    sfor<1, PNB>([&](auto b_) {
-      constexpr int b = decltype(b_)::value;
-      constexpr int ax = pipe_axis(b);
+    chain_forward([&](auto ax_, int b) {
+      constexpr int ax = decltype(ax_)::value;
       sv a = pipe_motion_to_child<ax>(sm[SM_SN + b], sm[SM_CS + b], pipe_len(b), acc);
       const float ua = vdot(lds3(&sm[SM_U + 6 * b]), a.a) + vdot(lds3(&sm[SM_U + 6 * b + 3]), a.l);
-      const float d = sm[SM_DINV + b] * (uh[b] - ua);
+      const float d = sm[SM_DINV + b] * (sm[SM_UH + 32 * b + lane] - ua);
       vaddk<ax>(a.a, d);
       acc = a;
-      col[5 + b] = d;
+      sm[SM_MCOL + 32 * (5 + b) + lane] = d;
     });
   }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------- contacts
@@ -790,16 +825,23 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_reset(
 }
 
 // warp per env: everything of the step after the arm half
-template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_step(SimParams P, const float* __restrict__ scratch, float* __restrict__ obs,
-                                                                             float* __restrict__ reward, unsigned char* __restrict__ done,
-                                                                             unsigned long long* __restrict__ counters) {
-  extern __shared__ float sm[];
+template <int ARM, int TASK> __global__ void __launch_bounds__(32 * PIH_PIPE_WARPS, PIH_PIPE_MIN_BLOCKS / PIH_PIPE_WARPS) k_pipe_step(SimParams P, const float* __restrict__ scratch,
+                                                                                               float* __restrict__ rowbuf, float* __restrict__ obs,
+                                                                                               float* __restrict__ reward, unsigned char* __restrict__ done,
+                                                                                               unsigned long long* __restrict__ counters) {
+  extern __shared__ float sm_all[];
   constexpr int nb = ArmDims<ARM>::NB;
   const ArmTables& T = c_arm[ARM];
-  const int e = blockIdx.x, lane = threadIdx.x;
+  // PIH_PIPE_WARPS envs per CTA, one warp each, each with its own SM_TOTAL floats of shared memory; the warps never
+  // synchronise with one another (only __syncwarp inside a warp)
+  const int lane = threadIdx.x & 31;
+  const int e = blockIdx.x * PIH_PIPE_WARPS + (threadIdx.x >> 5);
+  if (e >= P.n) return;
+  float* sm = sm_all + (threadIdx.x >> 5) * SM_TOTAL;
   const unsigned FULL = 0xffffffffu;
   float* w = sm + SM_SW;
   float* pa = sm + SM_PA;
+  float* rows_g = rowbuf + (size_t)e * kRowBufWords;     // this env's constraint rows (global scratch, L1/L2 resident)
   // ---- load: lane l fetches state slot l (one float4) and two float4 of the scratch block
   {
     const float4 v = P.state[(size_t)lane * P.n + e];
@@ -813,8 +855,6 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_step(S
     }
   }
   __syncwarp();
-  EnvState S;
-  envstate_from_words(w, S);
   PipeBase B;
   float qj, qdj;
   pipe_from_words(w, lane, B, qj, qdj);
@@ -824,22 +864,19 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_step(S
   unsigned char dn;
   if (pa[PA_ACTIVE] == 0.0f) {
     // frozen env (done, not reset): outputs re-emitted from the frozen state (base_env.py:61-71)
+    EnvState S;
+    envstate_from_words(w, S);
     observe<ARM>(S, off, o);
     rew = (S.flags & PIH_FLAG_SUCCESS) ? 1.0f : 0.0f;
     dn = 1;
   } else {
     const float dt = P.dt, idt = P.idt;
-    if (TASK == PIH_TASK_SCRIPTED) {
-      S.fsm_state = __float_as_int(pa[PA_FSM_STATE]); S.fsm_t = __float_as_int(pa[PA_FSM_T]);
-#pragma unroll
-      for (int k = 0; k < 7; ++k) S.mtgt[k] = pa[PA_MTGT + k];
-      S.grasp_ang = pa[PA_GRASP_ANG];
-    }
     const bool fsm_done = pa[PA_FSM_DONE] != 0.0f;
+    const int fsm_now = (TASK == PIH_TASK_SCRIPTED) ? __float_as_int(pa[PA_FSM_STATE]) : 0;
     // ---- pipe kinematics and dynamics
     pipe_fk(sm, B, lane, qj);
-    float vstar, col[PND];
-    pipe_dynamics(sm, B, lane, qdj, dt, (float)PIH_GRAVITY, vstar, col);
+    float vstar;
+    pipe_dynamics(sm, B, lane, qdj, dt, (float)PIH_GRAVITY, vstar);
     // ---- arm rows: lane j < nb owns joint j (its row of M^-1, motor and limit rows)
     const int ja = lane < nb ? lane : 0;
     float MinvA[nb];
@@ -851,14 +888,10 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_step(S
     {
       float qt = pa[PA_QSTAR + ja];
       const float lo = T.lo[ja], hi = T.hi[ja];
-      float qa = 0.0f;
-#pragma unroll
-      for (int j = 0; j < nb; ++j) qa = (ja == j) ? S.q[j] : qa;
+      const float qa = w[PIH_S_Q + ja];
       qt = (qt < lo) ? lo : ((qt > hi) ? hi : qt);
       const float vst = pa[PA_KP + ja] * (qt - qa) * idt;
-      float dg = 0.0f;
-#pragma unroll
-      for (int j = 0; j < nb; ++j) dg = (ja == j) ? MinvA[j] : dg;
+      const float dg = pa[PA_MINV + 10 * ja];
       m_diag = dg;
       m_dinv = 1.0f / dg;
       m_b = (vst - vsa) * m_dinv;
@@ -877,16 +910,17 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_step(S
     }
     const unsigned lim_mask0 = __ballot_sync(FULL, l_on0), lim_mask1 = __ballot_sync(FULL, l_on1);
     // ---- pipe joint motors: lane c = 5 + b owns the motor of joint b
-    float pm_diag = 1.0f;
-#pragma unroll
-    for (int c = 0; c < PND; ++c) pm_diag = (lane == c) ? col[c] : pm_diag;
+    const float pm_diag = (lane < PND) ? sm[SM_MCOL + 33 * lane] : 1.0f;      // M^-1[lane][lane]
     const float pm_dinv = 1.0f / pm_diag;
     const float pm_b = (0.0f - vstar) * pm_dinv;
     float pm_lam = 0.0f;
-    // ---- contacts: lane s owns segment s; then the slot-major compaction the oracle defines
+    // ---- contacts: lane s owns segment s; then the slot-major compaction the oracle defines.  (SM_UH, which aliases the
+    //      contact list, is dead: pipe_dynamics ended with a __syncwarp.)
     int ncon = 0, narmc = 0, pairmask = 0;
-    if (TASK == PIH_TASK_SCRIPTED && grasp_active(TASK, S.fsm_state)) {
+    if (TASK == PIH_TASK_SCRIPTED && grasp_active(TASK, fsm_now)) {
       // grasp constraint of the scripted task (peg_in_hole.py:99-104): first row set, bilateral, along the env axes
+      EnvState S;
+      envstate_from_words(w, S);
       FK<ARM> Fa;
       fk<ARM, nb>(S.q, Fa);
       v3 pee; m3 Ree;
@@ -964,191 +998,218 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_step(S
     }
     __syncwarp();
     // ---- contact rows: for every contact and direction, lane i computes entry i of the Jacobian row, then of M^-1 J^T
-    // per-lane kinematic data of "its" dof: joint b = lane - 5 (axis and origin in the env frame), arm joint j = lane
-    const int jb = (lane >= 6 && lane < PND) ? lane - 5 : 1;
-    const int jax = (jb & 1) ? 2 : 0;                  // joint axis of body jb: column jax of its rotation
-    const v3 axw = mk(sm[SM_RW + 9 * jb + jax], sm[SM_RW + 9 * jb + 3 + jax], sm[SM_RW + 9 * jb + 6 + jax]);
-    const v3 ob = lds3(&sm[SM_PW + 3 * jb]);
-    const m3 R0 = ldsm(&sm[SM_RW]);
-    const v3 p0 = lds3(&sm[SM_PW]);
-    const v3 zja = lds3(&pa[PA_ZJ + 3 * ja]), pja = lds3(&pa[PA_PW + 3 * ja]);
-    const int jt_a = T.jtype[ja];
-    for (int k = 0; k < ncon; ++k) {
-      const float* cd = &sm[SM_CON + 12 * k];
-      const v3 cp = lds3(cd), cn = lds3(cd + 3);
-      const float cdist = cd[6];
-      const int cpair = __float_as_int(cd[8]), cseg = __float_as_int(cd[9]), carm = __float_as_int(cd[10]), aslot = __float_as_int(cd[11]);
-      pairmask |= cpair;
-      const bool has_pipe = cseg >= 0, has_arm = carm >= 0;
-      v3 dir[3];
-      const bool weld = TASK == PIH_TASK_SCRIPTED && cpair == PIH_PAIR_GRASP;
-      if (weld) { dir[0] = mk(1.0f, 0.0f, 0.0f); dir[1] = mk(0.0f, 1.0f, 0.0f); dir[2] = mk(0.0f, 0.0f, 1.0f); }
-      else { dir[0] = cn; plane_space(cn, dir[1], dir[2]); }
-      const int Lb = has_pipe ? seg_body(cseg) : 0;
-      const unsigned anc = has_arm ? T.anc[carm] : 0u;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const int r = 3 * k + d;
-        float Jp = 0.0f, MJp = 0.0f, Ja = 0.0f, MJa = 0.0f;
-        if (has_pipe) {
-          const v3 rb = vsub(cp, p0);
-          const v3 jang = mTv(R0, vcross(rb, dir[d]));
-          const v3 jlin = mTv(R0, dir[d]);
-          const float jj = vdot(dir[d], vcross(axw, vsub(cp, ob)));
-          Jp = (lane < 3) ? vgetr(jang, lane) : ((lane < 6) ? vgetr(jlin, lane - 3) : ((lane < PND && lane - 5 <= Lb) ? jj : 0.0f));
-          sm[SM_J + 32 * r + lane] = Jp;
-          __syncwarp();
-          float s = 0.0f;
-#pragma unroll
-          for (int i = 0; i < PND; ++i) s = fmaf(col[i], sm[SM_J + 32 * r + i], s);
-          MJp = (lane < PND) ? s : 0.0f;
-          sm[SM_MJ + 32 * r + lane] = MJp;
-        }
-        if (has_arm) {
-          const float sg = has_pipe ? -1.0f : 1.0f;
-          float v = 0.0f;
-          if (lane < nb && ((anc >> lane) & 1u)) {
-            if (jt_a == 0) v = vdot(dir[d], vcross(zja, vsub(cp, pja)));
-            else v = vdot(dir[d], zja);
-            v = sg * v;
+    {
+      // per-lane kinematic data of "its" dof: joint b = lane - 5 (axis and origin in the env frame), arm joint j = lane
+      const int jb = (lane >= 6 && lane < PND) ? lane - 5 : 1;
+      const int jax = (jb & 1) ? 2 : 0;                  // joint axis of body jb: column jax of its rotation
+      const v3 axw = mk(sm[SM_RW + 9 * jb + jax], sm[SM_RW + 9 * jb + 3 + jax], sm[SM_RW + 9 * jb + 6 + jax]);
+      const v3 ob = lds3(&sm[SM_PW + 3 * jb]);
+      const m3 R0 = ldsm(&sm[SM_RW]);
+      const v3 p0 = lds3(&sm[SM_PW]);
+      const v3 zja = lds3(&pa[PA_ZJ + 3 * ja]), pja = lds3(&pa[PA_PW + 3 * ja]);
+      const int jt_a = T.jtype[ja];
+      float* jt = &sm[SM_JTMP];
+#pragma unroll 1
+      for (int k = 0; k < ncon; ++k) {
+        const float* cd = &sm[SM_CON + 12 * k];
+        const v3 cp = lds3(cd), cn = lds3(cd + 3);
+        const float cdist = cd[6];
+        const int cpair = __float_as_int(cd[8]), cseg = __float_as_int(cd[9]), carm = __float_as_int(cd[10]);
+        pairmask |= cpair;
+        const bool has_pipe = cseg >= 0, has_arm = carm >= 0;
+        v3 dir[3];
+        const bool weld = TASK == PIH_TASK_SCRIPTED && cpair == PIH_PAIR_GRASP;
+        if (weld) { dir[0] = mk(1.0f, 0.0f, 0.0f); dir[1] = mk(0.0f, 1.0f, 0.0f); dir[2] = mk(0.0f, 0.0f, 1.0f); }
+        else { dir[0] = cn; plane_space(cn, dir[1], dir[2]); }
+        const int Lb = has_pipe ? seg_body(cseg) : 0;
+        const unsigned anc = has_arm ? T.anc[carm] : 0u;
+#pragma unroll 1
+        for (int d = 0; d < 3; ++d) {
+          const int r = 3 * k + d;
+          const v3 dd = (d == 0) ? dir[0] : ((d == 1) ? dir[1] : dir[2]);
+          float* rg = rows_g + (size_t)r * kRowWords;
+          float Jp = 0.0f, MJp = 0.0f, Ja = 0.0f, MJa = 0.0f;
+          if (has_pipe) {
+            const v3 rb = vsub(cp, p0);
+            const v3 jang = mTv(R0, vcross(rb, dd));
+            const v3 jlin = mTv(R0, dd);
+            const float jj = vdot(dd, vcross(axw, vsub(cp, ob)));
+            Jp = (lane < 3) ? vgetr(jang, lane) : ((lane < 6) ? vgetr(jlin, lane - 3) : ((lane < PND && lane - 5 <= Lb) ? jj : 0.0f));
+            jt[lane] = Jp;
+            __syncwarp();
+            // entries beyond the contact's body are structural zeros: fma(x, 0, s) == s, so the sum stops at 5 + Lb
+            float s = 0.0f;
+            const int iend = 6 + Lb;
+#pragma unroll 2
+            for (int i = 0; i < iend; ++i) s = fmaf(sm[SM_MCOL + 32 * i + lane], jt[i], s);
+            MJp = (lane < PND) ? s : 0.0f;
+            rg[lane] = Jp; rg[32 + lane] = MJp;
+            __syncwarp();
           }
-          Ja = v;
-          if (lane < 16) sm[SM_JA + 16 * (3 * aslot + d) + lane] = Ja;
-          __syncwarp();
-          float s = 0.0f;
+          if (has_arm) {
+            const float sg = has_pipe ? -1.0f : 1.0f;
+            float v = 0.0f;
+            if (lane < nb && ((anc >> lane) & 1u)) {
+              if (jt_a == 0) v = vdot(dd, vcross(zja, vsub(cp, pja)));
+              else v = vdot(dd, zja);
+              v = sg * v;
+            }
+            Ja = v;
+            if (lane < 16) jt[32 + lane] = Ja;
+            __syncwarp();
+            float s = 0.0f;
 #pragma unroll
-          for (int j = 0; j < nb; ++j) s = fmaf(MinvA[j], sm[SM_JA + 16 * (3 * aslot + d) + j], s);
-          MJa = (lane < nb) ? s : 0.0f;
-          if (lane < 16) sm[SM_MJA + 16 * (3 * aslot + d) + lane] = MJa;
+            for (int j = 0; j < nb; ++j) s = fmaf(MinvA[j], jt[32 + j], s);
+            MJa = (lane < nb) ? s : 0.0f;
+            if (lane < 16) { rg[64 + lane] = Ja; rg[80 + lane] = MJa; }
+            __syncwarp();
+          }
+          float pd = 0.0f, pv = 0.0f;
+          if (has_pipe && lane < PND) { pd = Jp * MJp; pv = Jp * vstar; }
+          if (has_arm && lane < nb) {
+            if (has_pipe) { pd = fmaf(Ja, MJa, pd); pv = fmaf(Ja, vsa, pv); }
+            else { pd = Ja * MJa; pv = Ja * vsa; }
+          }
+          const float diag = bfly32(pd), vrel = bfly32(pv);
+          const float dinv = 1.0f / diag;
+          float tv = 0.0f;
+          if (weld) tv = -((float)PIH_ERP * (d == 0 ? cn.x : (d == 1 ? cn.y : cn.z)) * idt);
+          else if (d == 0) tv = (cdist > 0.0f) ? -(cdist * idt) : -((float)PIH_ERP * cdist * idt);
+          float* rs = &sm[SM_ROWS + 4 * r];
+          rs[0] = dinv; rs[1] = diag; rs[2] = (tv - vrel) * dinv; rs[3] = 0.0f;      // (every lane writes the same values)
         }
-        float pd = 0.0f, pv = 0.0f;
-        if (has_pipe && lane < PND) { pd = Jp * MJp; pv = Jp * vstar; }
-        if (has_arm && lane < nb) {
-          if (has_pipe) { pd = fmaf(Ja, MJa, pd); pv = fmaf(Ja, vsa, pv); }
-          else { pd = Ja * MJa; pv = Ja * vsa; }
-        }
-        const float diag = bfly32(pd), vrel = bfly32(pv);
-        const float dinv = 1.0f / diag;
-        float tv = 0.0f;
-        if (weld) tv = -((float)PIH_ERP * (d == 0 ? cn.x : (d == 1 ? cn.y : cn.z)) * idt);
-        else if (d == 0) tv = (cdist > 0.0f) ? -(cdist * idt) : -((float)PIH_ERP * cdist * idt);
-        float* rs = &sm[SM_ROWS + 4 * r];
-        rs[0] = dinv; rs[1] = diag; rs[2] = (tv - vrel) * dinv; rs[3] = 0.0f;      // (every lane writes the same values)
       }
     }
     __syncwarp();
     // ---- projected Gauss-Seidel, one island: arm motors, arm limits, pipe motors, contact normals, contact friction
     float dva = 0.0f, dvp = 0.0f;
     int st_it = 0;
+    // which contacts involve the pipe / the arm, as bit masks in registers (no shared-memory look-up on the row's critical path)
+    unsigned long long mpipe = 0ull, marm = 0ull;
+    static_assert(PIH_PIPE_MAXC <= 64, "contact masks are 64-bit");
+    for (int k = 0; k < ncon; ++k) {
+      mpipe |= (unsigned long long)(__float_as_int(sm[SM_CON + 12 * k + 9]) >= 0) << k;
+      marm |= (unsigned long long)(__float_as_int(sm[SM_CON + 12 * k + 10]) >= 0) << k;
+    }
+    const int nrow = 3 * ncon;
+    // Row t of a sweep: the normals of all contacts first (t < ncon), then the two friction rows of each contact.  Its
+    // coefficients live in the global row block; they are fetched ONE ROW AHEAD so that the L2 latency of row t + 1
+    // hides behind the butterfly of row t (the shared-memory carve-out leaves little L1 for them).
+    struct RowRegs { float j, mj, ja, mja; };
+    auto fetch = [&](int t, RowRegs& q) {
+      q.j = 0.0f; q.mj = 0.0f; q.ja = 0.0f; q.mja = 0.0f;
+      if (t < nrow) {
+        const int u = t - ncon;
+        const int k = (t < ncon) ? t : (u >> 1), d = (t < ncon) ? 0 : 1 + (u & 1);
+        const float* rg = rows_g + (size_t)(3 * k + d) * kRowWords;
+        if ((mpipe >> k) & 1ull) { q.j = rg[lane]; q.mj = rg[32 + lane]; }
+        if (((marm >> k) & 1ull) && lane < nb) { q.ja = rg[64 + lane]; q.mja = rg[80 + lane]; }
+      }
+    };
+#pragma unroll 1
     for (int it = 0; it < P.solver_iters; ++it) {
       float res = 0.0f;
-      // arm motors: the owner lane solves its row, the impulse is broadcast
-#pragma unroll
-      for (int j = 0; j < nb; ++j) {
-        float dl = fmaf(-dva, m_dinv, m_b);
+      RowRegs nxt;
+      fetch(0, nxt);                  // in flight while the motor rows are solved
+      // Motor and limit rows.  Every lane evaluates "its" row formula at every row step, but only the owner's value is
+      // used (broadcast by the shuffle).  A lane owns each of its rows ONCE per sweep, so its accumulated impulse, the
+      // clamp interval derived from it and its residual are handled outside the row steps: a row step is FFMA, two
+      // FMNMX, a select, the shuffle and the velocity update - the dependent chain of the sweep.  (fminf / fmaxf against
+      // the oracle's ternaries: same values; the rigid-peg kernels rely on the same equivalence.)
+      {
         const float dlo = -m_max - m_lam, dhi = m_max - m_lam;
-        dl = (dl < dlo) ? dlo : dl;
-        dl = (dl > dhi) ? dhi : dl;
-        if (lane == j) {
-          m_lam = m_lam + dl;
-          float rv = dl * m_diag;
-          rv = rv * rv;
-          res = (rv > res) ? rv : res;
+        float dl_own = 0.0f;
+#pragma unroll
+        for (int j = 0; j < nb; ++j) {
+          float dl = fminf(fmaxf(fmaf(-dva, m_dinv, m_b), dlo), dhi);
+          dl_own = (lane == j) ? dl : dl_own;
+          dl = __shfl_sync(FULL, dl, j);
+          dva = fmaf(MinvA[j], dl, dva);
         }
-        dl = __shfl_sync(FULL, dl, j);
-        dva = fmaf(MinvA[j], dl, dva);
+        m_lam = m_lam + dl_own;                     // (lanes >= nb own nothing: their values are never read)
+        float rv = dl_own * m_diag;
+        rv = rv * rv;
+        res = (lane < nb && rv > res) ? rv : res;
       }
       if (lim_mask0 | lim_mask1) {
+        float dl0_own = 0.0f, dl1_own = 0.0f;
 #pragma unroll
         for (int j = 0; j < nb; ++j) {
           if ((lim_mask0 >> j) & 1u) {
-            float dl = fmaf(-dva, m_dinv, l_b0);
-            const float dlo = -l_lam0;
-            dl = (dl < dlo) ? dlo : dl;
-            if (lane == j) {
-              l_lam0 = l_lam0 + dl;
-              float rv = dl * m_diag;
-              rv = rv * rv;
-              res = (rv > res) ? rv : res;
-            }
+            float dl = fmaxf(fmaf(-dva, m_dinv, l_b0), -l_lam0);
+            dl0_own = (lane == j) ? dl : dl0_own;
             dl = __shfl_sync(FULL, dl, j);
             dva = fmaf(MinvA[j], dl, dva);
           }
           if ((lim_mask1 >> j) & 1u) {
-            float dl = fmaf(-(-1.0f * dva), m_dinv, l_b1);
-            const float dlo = -l_lam1;
-            dl = (dl < dlo) ? dlo : dl;
-            if (lane == j) l_lam1 = l_lam1 + dl;
+            float dl = fmaxf(fmaf(-(-1.0f * dva), m_dinv, l_b1), -l_lam1);
+            dl1_own = (lane == j) ? dl : dl1_own;
             dl = dl * -1.0f;
-            if (lane == j) {
-              float rv = dl * m_diag;
-              rv = rv * rv;
-              res = (rv > res) ? rv : res;
-            }
             dl = __shfl_sync(FULL, dl, j);
             dva = fmaf(MinvA[j], dl, dva);
           }
         }
+        l_lam0 = l_lam0 + dl0_own; l_lam1 = l_lam1 + dl1_own;
+        float r0 = dl0_own * m_diag, r1 = (dl1_own * -1.0f) * m_diag;
+        r0 = r0 * r0; r1 = r1 * r1;
+        res = (l_on0 && r0 > res) ? r0 : res;
+        res = (l_on1 && r1 > res) ? r1 : res;
       }
-      // pipe joint motors
-      sfor<1, PNB>([&](auto b_) {
-        constexpr int c = 5 + decltype(b_)::value;
-        float dl = fmaf(-dvp, pm_dinv, pm_b);
+      // pipe joint motors: lane c = 5 + b owns joint b; its column of M^-1 comes from shared memory with an immediate offset
+      {
         const float dlo = (float)(-PIH_PIPE_MOTOR_IMPULSE) - pm_lam, dhi = (float)PIH_PIPE_MOTOR_IMPULSE - pm_lam;
-        dl = (dl < dlo) ? dlo : dl;
-        dl = (dl > dhi) ? dhi : dl;
-        if (lane == c) {
-          pm_lam = pm_lam + dl;
-          float rv = dl * pm_diag;
-          rv = rv * rv;
-          res = (rv > res) ? rv : res;
+        float dl_own = 0.0f;
+        const float* mcol = &sm[SM_MCOL + lane];
+#pragma unroll
+        for (int c = 6; c < PND; ++c) {
+          float dl = fminf(fmaxf(fmaf(-dvp, pm_dinv, pm_b), dlo), dhi);
+          dl_own = (lane == c) ? dl : dl_own;
+          dl = __shfl_sync(FULL, dl, c);
+          dvp = fmaf(mcol[32 * c], dl, dvp);
         }
-        dl = __shfl_sync(FULL, dl, c);
-        dvp = fmaf(col[c], dl, dvp);
-      });
+        pm_lam = pm_lam + dl_own;
+        float rv = dl_own * pm_diag;
+        rv = rv * rv;
+        res = (lane >= 6 && lane < PND && rv > res) ? rv : res;
+      }
       // contacts: normals, then friction
 #pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass)
-#pragma unroll 1
-        for (int k = 0; k < ncon; ++k) {
-          const float* cd = &sm[SM_CON + 12 * k];
-          const float mu = cd[7];
-          const int cseg = __float_as_int(cd[9]), carm = __float_as_int(cd[10]), aslot = __float_as_int(cd[11]);
-          const bool has_pipe = cseg >= 0, has_arm = carm >= 0;
-          for (int d = (pass ? 1 : 0); d < (pass ? 3 : 1); ++d) {
-            const int r = 3 * k + d;
-            float p = 0.0f;
-            if (has_pipe) p = sm[SM_J + 32 * r + lane] * dvp;
-            if (has_arm && lane < nb) {
-              const float ja_ = sm[SM_JA + 16 * (3 * aslot + d) + lane];
-              p = has_pipe ? fmaf(ja_, dva, p) : ja_ * dva;
-            }
-            const float rel = bfly32(p);
-            float* rs = &sm[SM_ROWS + 4 * r];
-            float dl = fmaf(-rel, rs[0], rs[2]);
-            const float lam = rs[3];
-            if (TASK == PIH_TASK_SCRIPTED && mu < 0.0f) {   // grasp constraint: bilateral, |impulse| <= maxForce dt
-              const float wl = (float)PIH_GRASP_MAX_FORCE * dt;
-              const float dlo = -wl - lam, dhi = wl - lam;
-              dl = (dl < dlo) ? dlo : dl;
-              dl = (dl > dhi) ? dhi : dl;
-            } else if (d == 0) {
-              const float dlo = -lam;
-              dl = (dl < dlo) ? dlo : dl;
-            } else {
-              const float lim = mu * sm[SM_ROWS + 4 * (3 * k) + 3];
-              const float dlo = -lim - lam, dhi = lim - lam;
-              dl = (dl < dlo) ? dlo : dl;
-              dl = (dl > dhi) ? dhi : dl;
-            }
-            rs[3] = lam + dl;      // (every lane writes the same value and later reads back its own write)
-            float rv = dl * rs[1];
-            rv = rv * rv;
-            res = (rv > res) ? rv : res;
-            if (has_pipe) dvp = fmaf(sm[SM_MJ + 32 * r + lane], dl, dvp);
-            if (has_arm && lane < nb) dva = fmaf(sm[SM_MJA + 16 * (3 * aslot + d) + lane], dl, dva);
-          }
+      for (int t = 0; t < nrow; ++t) {
+        const RowRegs cur = nxt;
+        fetch(t + 1, nxt);
+        const int u = t - ncon;
+        const int k = (t < ncon) ? t : (u >> 1), d = (t < ncon) ? 0 : 1 + (u & 1);
+        const bool has_pipe = (mpipe >> k) & 1ull, has_arm = (marm >> k) & 1ull;
+        const int r = 3 * k + d;
+        float* rs = &sm[SM_ROWS + 4 * r];
+        const float rdinv = rs[0], rdiag = rs[1], rb = rs[2], lam = rs[3];
+        const float mu = sm[SM_CON + 12 * k + 7], lam0 = sm[SM_ROWS + 12 * k + 3];
+        float p = 0.0f;
+        if (has_pipe) p = cur.j * dvp;
+        if (has_arm && lane < nb) p = has_pipe ? fmaf(cur.ja, dva, p) : cur.ja * dva;
+        const float rel = bfly32(p);
+        float dl = fmaf(-rel, rdinv, rb);
+        if (TASK == PIH_TASK_SCRIPTED && mu < 0.0f) {   // grasp constraint: bilateral, |impulse| <= maxForce dt
+          const float wl = (float)PIH_GRASP_MAX_FORCE * dt;
+          const float dlo = -wl - lam, dhi = wl - lam;
+          dl = (dl < dlo) ? dlo : dl;
+          dl = (dl > dhi) ? dhi : dl;
+        } else if (d == 0) {
+          const float dlo = -lam;
+          dl = (dl < dlo) ? dlo : dl;
+        } else {
+          const float lim = mu * lam0;
+          const float dlo = -lim - lam, dhi = lim - lam;
+          dl = (dl < dlo) ? dlo : dl;
+          dl = (dl > dhi) ? dhi : dl;
         }
+        rs[3] = lam + dl;      // (every lane writes the same value and later reads back its own write)
+        float rv = dl * rdiag;
+        rv = rv * rv;
+        res = (rv > res) ? rv : res;
+        if (has_pipe) dvp = fmaf(cur.mj, dl, dvp);
+        if (has_arm && lane < nb) dva = fmaf(cur.mja, dl, dva);
+      }
       st_it += 1;
       // residual of the iteration: max over the lanes (non-negative floats order like their bit patterns)
       const unsigned rmax = __reduce_max_sync(FULL, __float_as_uint(res));
@@ -1165,7 +1226,15 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(32) k_pipe_step(S
         atomicMax(&P.stats[PIH_STAT_PGS_ITERS_MAX], (unsigned long long)st_it);
       }
     }
-    // ---- integrate.  Arm: every lane integrates all joints (the full EnvState stays identical in all lanes).
+    // ---- integrate.  Arm: every lane integrates all joints (the full EnvState is identical in all lanes from here on).
+    EnvState S;
+    envstate_from_words(w, S);
+    if (TASK == PIH_TASK_SCRIPTED) {
+      S.fsm_state = __float_as_int(pa[PA_FSM_STATE]); S.fsm_t = __float_as_int(pa[PA_FSM_T]);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) S.mtgt[k] = pa[PA_MTGT + k];
+      S.grasp_ang = pa[PA_GRASP_ANG];
+    }
 #pragma unroll
     for (int j = 0; j < nb; ++j) {
       const float vsj = __shfl_sync(FULL, vsa, j), dvj = __shfl_sync(FULL, dva, j);

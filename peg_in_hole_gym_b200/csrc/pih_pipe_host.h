@@ -7,7 +7,7 @@ namespace pih { struct SimParams; }
 
 // uploads this translation unit's copy of the model tables to the current device
 cudaError_t pih_pipe_upload_tables();
-// bytes of the per-env scratch block between the two kernels of a pipe step
+// bytes of the per-env scratch: the block handed from k_pipe_arm to k_pipe_step + the solver's constraint rows
 size_t pih_pipe_scratch_bytes(int num_envs);
 // PegInHole.reset with the pipe (mask nullable)
 void pih_pipe_launch_reset(const pih::SimParams& P, const unsigned char* mask, float* obs, cudaStream_t st);
