@@ -187,7 +187,8 @@ def config5_sweep(args, rank, world, local, dev, reduce_max, barrier):
         n = total // world
         sim = BatchedSim(n, sub_num=total, env_id_base=rank * n, offset=OFFSET, seed=SEED, max_steps=MAX_STEPS, auto_reset=True, device=local)
         sim.reset()
-        sim.rollout(8, count=False)
+        sim.rollout(60, count=False)                  # 60 steps into the 200-step episodes
+        state0 = sim.state.clone()                    # every mode steps the SAME 30 states (the step cost drifts with the episode phase)
         offs = torch.zeros(n, 4, device=dev)
         offs[:, :3] = sim.env_offsets_device()
         g = torch.Generator(device=dev); g.manual_seed(99 + rank)
@@ -203,9 +204,10 @@ def config5_sweep(args, rank, world, local, dev, reduce_max, barrier):
                     sim.step(a)
                     if mode == "nccl":
                         gather_rows_to_rank0(pack_rows(sim.obs, sim.reward, sim.done.float()), counts=[n] * world)
+            sim.state.copy_(state0)
             for i in range(warm):
                 one(i)
-            ms = timed_steps(one, steps, barrier, torch)
+            ms = timed_steps(lambda i: one(warm + i), steps, barrier, torch)
             if mode == "peer" and rank == 0:
                 peer.wait(); peer.check()
             ms = reduce_max(ms)

@@ -243,10 +243,17 @@ struct StepSignal {
   const unsigned* wait_flags; int wait_count; unsigned wait_value; unsigned long long timeout_ns; unsigned* timed_out;
 };
 // bounded spin of one thread on one flag word (steps count up, so >=); records the index of a flag that never came
-PIH_D void wait_flag(const volatile unsigned* flag, unsigned value, unsigned long long timeout_ns, unsigned* timed_out, int idx) {
+// acquire load at system scope: what the flag's writer (a kernel on another GPU) released is visible after it - without a
+// full system fence on the waiting side
+PIH_D unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+PIH_D void wait_flag(const unsigned* flag, unsigned value, unsigned long long timeout_ns, unsigned* timed_out, int idx) {
   unsigned long long t0, t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  while ((int)(*flag - value) < 0) {
+  while ((int)(ld_acquire_sys(flag) - value) < 0) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     if (t - t0 > timeout_ns) { atomicExch(timed_out, 1u + (unsigned)idx); break; }
     __nanosleep(100);
@@ -266,7 +273,6 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(64, 1) k_step_ws(
     // learner rank: the rows of the previous step of every rank must have landed before this step's rows may follow
     // (the consumer's wait, folded into its next launch instead of a kernel of its own)
     if ((int)threadIdx.x < sig.wait_count) wait_flag(sig.wait_flags + threadIdx.x, sig.wait_value, sig.timeout_ns, sig.timed_out, threadIdx.x);
-    __threadfence_system();
     __syncthreads();
   }
   // the action row is requested first: with zero-copy host buffers it comes over PCIe, and the state load and the
@@ -447,7 +453,7 @@ __global__ void k_signal_flag(volatile unsigned* flag, unsigned value) {
   __threadfence_system();
 }
 // waits until every flag has reached `value` (steps count up, so >=); gives up after `timeout_ns` and records it
-__global__ void k_wait_flags(const volatile unsigned* flags, int count, unsigned value, unsigned long long timeout_ns, unsigned* timed_out) {
+__global__ void k_wait_flags(const unsigned* flags, int count, unsigned value, unsigned long long timeout_ns, unsigned* timed_out) {
   const int i = threadIdx.x;
   if (i < count) wait_flag(flags + i, value, timeout_ns, timed_out, i);
   __threadfence_system();
@@ -504,6 +510,7 @@ struct pih_handle {
   size_t bind_bytes[PIH_ALIAS_SLOTS];
   char* bind_dev[PIH_ALIAS_SLOTS];
   int n_bind, no_zero_copy;
+  float* d_stage;            // large batches with a learner buffer: local [obs n*5 | reward n | done n] block the rows are copied from
   int pipe;                  // peg_model == PIH_PEG_PIPE: the flexible-pipe kernels (pih_pipe.cu)
   float* d_pipe_scratch;     // per-env block between k_pipe_arm and k_pipe_step
   unsigned* d_cta_counter;   // fused step signal: CTAs that have delivered their rows (re-armed by the last one)
@@ -634,10 +641,10 @@ int pih_create(const pih_config* cfg, void* state_dev, pih_handle** out) {
   P.state = reinterpret_cast<float4*>(state_dev);
   h->block = 32;
   // warp-specialised kernels while a 64-thread CTA per 32 envs fits the register file (4 CTAs x 64 x 255 registers per
-  // SM): measured faster than the classic kernels up to 16384 envs for both arms (tools/ws_threshold_probe.py), slower
+  // SM): measured faster than the classic kernels up to 16384 envs for both arms (round 1, profiles/r01_summary.md), slower
   // from 24576 envs on, where the classic kernels' one warp per 32 envs fills the schedulers first
   h->ws = (P.n <= 148 * 32 * 4) ? 1 : 0;
-  // measured (tools/split_probe.py): fused 216 / 434 / 781 us against split 196 / 378 / 692 us per step at 65536 /
+  // measured (round 1, profiles/r01_summary.md): fused 216 / 434 / 781 us against split 196 / 378 / 692 us per step at 65536 /
   // 131072 / 262144 envs; below ~2 waves of the fused kernel the extra launch does not pay (104 vs 106 us at 32768)
   h->split = (P.n >= 49152) ? 1 : 0;
   if (cfg->kernel_family == PIH_KERNELS_WARP_SPECIALISED) { h->ws = 1; h->split = 0; }
@@ -661,6 +668,7 @@ void pih_destroy(pih_handle* h) {
   if (!h) return;
   if (h->d_cta_counter) cudaFree(h->d_cta_counter);
   if (h->d_pipe_scratch) cudaFree(h->d_pipe_scratch);
+  if (h->d_stage) cudaFree(h->d_stage);
   if (h->d_qt) cudaFree(h->d_qt);
   if (h->h_action) cudaFreeHost(h->h_action);
   if (h->h_obs) cudaFreeHost(h->h_obs);     // one pinned block: obs | reward | done
@@ -780,10 +788,19 @@ static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, flo
   sig.cta_counter = h->d_cta_counter;
   uint32_t* const flag_dev = sig.flag;
   const uint32_t flag_value = sig.value;
+  // signalled step of a large batch: the kernels write a local block, one copy kernel delivers it and publishes the flag
+  float* const out_obs = obs_dev; float* const out_rew = reward_dev; uint8_t* const out_done = done_dev;
+  const bool staged_rows = flag_dev && !h->ws && obs_dev && reward_dev && done_dev;
+  if (staged_rows) {
+    const size_t n = (size_t)h->P.n;
+    if (!h->d_stage && cudaMalloc(&h->d_stage, n * 24 + ((n + 15) & ~(size_t)15)) != cudaSuccess)
+      return fail(h, PIH_ERR_CUDA, "row stage allocation", cudaGetLastError());
+    obs_dev = h->d_stage; reward_dev = h->d_stage + 5 * n; done_dev = reinterpret_cast<uint8_t*>(h->d_stage + 6 * n);
+  }
   if (h->pipe) {
     if (sig.wait_flags) k_wait_flags<<<1, 64, 0, (cudaStream_t)stream>>>(sig.wait_flags, sig.wait_count, sig.wait_value, sig.timeout_ns, sig.timed_out);
     pih_pipe_launch_step(h->P, action_dev, h->d_pipe_scratch, obs_dev, reward_dev, done_dev, nullptr, (cudaStream_t)stream);
-    if (flag_dev) k_signal_flag<<<1, 1, 0, (cudaStream_t)stream>>>(flag_dev, flag_value);
+    if (flag_dev && !staged_rows) k_signal_flag<<<1, 1, 0, (cudaStream_t)stream>>>(flag_dev, flag_value);
   } else if (h->ws) { LAUNCH_WS(k_step_ws, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev, sig); }
   else {
     // large batches: the wait and the signal are launches of their own (noise next to a multi-hundred-microsecond step)
@@ -796,7 +813,24 @@ static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, flo
     } else {
       LAUNCH(k_step, h, stream, h->P, action_dev, obs_dev, reward_dev, done_dev);
     }
-    if (flag_dev) k_signal_flag<<<1, 1, 0, (cudaStream_t)stream>>>(flag_dev, flag_value);   // large batches: the extra launch is noise
+    if (flag_dev && !staged_rows) k_signal_flag<<<1, 1, 0, (cudaStream_t)stream>>>(flag_dev, flag_value);
+  }
+  if (staged_rows) {
+    // Large batches: the (obs, reward, done) rows reach the learner buffer as a device-to-device copy after the step (the
+    // copy engine moves the 13 MB of 524288 envs over NVLink in ~40 us; per-thread peer stores inside the step kernel
+    // cost 180 us, a copy kernel with word stores 200 us), then a one-thread kernel publishes the flag.  One copy when the
+    // destination slices are laid out like the local block (PeerLearnerBuffer's layout), else three.
+    const size_t n = (size_t)h->P.n;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t cc;
+    if (out_rew == out_obs + 5 * n && out_done == reinterpret_cast<uint8_t*>(out_rew + n)) cc = cudaMemcpyAsync(out_obs, obs_dev, n * 25, cudaMemcpyDeviceToDevice, st);
+    else {
+      cc = cudaMemcpyAsync(out_obs, obs_dev, n * 20, cudaMemcpyDeviceToDevice, st);
+      if (cc == cudaSuccess) cc = cudaMemcpyAsync(out_rew, reward_dev, n * 4, cudaMemcpyDeviceToDevice, st);
+      if (cc == cudaSuccess) cc = cudaMemcpyAsync(out_done, done_dev, n, cudaMemcpyDeviceToDevice, st);
+    }
+    if (cc != cudaSuccess) return fail(h, PIH_ERR_CUDA, "row copy to the learner buffer", cc);
+    k_signal_flag<<<1, 1, 0, st>>>(flag_dev, flag_value);
   }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_step launch", ce);
