@@ -47,9 +47,11 @@ typedef struct pih_config {
   int32_t action_frame_env; /* NEW 0 = reference (actions are absolute world coordinates), 1 = relative to env origin */
   int32_t device;           /* CUDA device ordinal */
   uint64_t seed;            /* Philox key (reference: unseeded global MT19937, peg_in_hole.py:239) */
-  int32_t kernel_family;    /* NEW which step kernels run: 0 = chosen from num_envs (default), 1 = warp-specialised small-batch kernels,
-                               2 = fused thread-per-env kernel, 3 = split apply_action + dynamics kernels.  All families compute the
-                               same bits (tests/test_gpu_parity.py); the field exists so that every family can be tested at any size */
+  int32_t kernel_family;    /* NEW which step kernels run: 0 = chosen from num_envs (default), 1 = warp-specialised small-batch kernels
+                               (three warps per 32 envs: action / dynamics / contacts), 2 = fused thread-per-env kernel, 3 = split
+                               apply_action + dynamics kernels, 4 = warp-specialised with two warps per 32 envs (action / dynamics).
+                               All families compute the same bits (tests/test_gpu_parity.py); the field exists so that every family
+                               can be tested at any size */
   int32_t host_path;        /* NEW pih_step_host: 0 = zero-copy when the caller's buffers are page-locked, else staged; 1 = always staged */
   int32_t peg_model;        /* what the reference's `pipe.urdf` object is simulated as (peg_in_hole.py:240-245): 0 = one rigid end
                                segment (the round-1 stand-in), 1 = the 25-link chain with 23 continuous joints (panda, tasks 0 and 2).
@@ -60,6 +62,7 @@ typedef struct pih_config {
 #define PIH_KERNELS_WARP_SPECIALISED 1
 #define PIH_KERNELS_FUSED 2
 #define PIH_KERNELS_SPLIT 3
+#define PIH_KERNELS_WARP_SPECIALISED_2 4
 
 typedef struct pih_handle pih_handle;
 
@@ -105,6 +108,20 @@ int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, floa
  * call, so a stale answer can never be used.  host_ptr == NULL in pih_host_unbind drops every binding. */
 int pih_host_bind(pih_handle* h, const void* host_ptr, uint64_t bytes);
 int pih_host_unbind(pih_handle* h, const void* host_ptr);
+
+/* Resident step server for the host-buffer path (NEW).  The reference's worker processes stay alive between steps and
+ * are fed through queues (base_env_mp.py:40-51,75-87); the counterpart here is ONE resident launch of the three-warp step
+ * kernel whose CTAs keep their envs' state on chip, wait for the host to publish a step in a page-locked control block,
+ * run it, write (obs, reward, done) into the bound host buffers and publish completion, on which pih_server_step spins:
+ * no kernel launch, no stream synchronisation and no state traffic per step.  Action-driven rigid-peg tasks, batches
+ * that fit one resident wave (<= 2 CTAs of 32 envs per SM).  obs/reward/done_host and every action_host must be
+ * page-locked and device-mapped (16-byte aligned).  The kernel retires itself after idle_timeout_ms without a step
+ * (0 = 200 ms) and is restarted transparently by the next pih_server_step; any other entry point of the handle retires
+ * it first (the state buffer is then current), and pih_server_step resumes it.  pih_server_step returns when the step's
+ * outputs are in the host buffers.  Same bits as pih_step. */
+int pih_server_start(pih_handle* h, float* obs_host, float* reward_host, uint8_t* done_host, uint32_t idle_timeout_ms, void* stream);
+int pih_server_step(pih_handle* h, const float* action_host);
+int pih_server_stop(pih_handle* h);
 
 /* Execution statistics (NEW; measurement only).  stats_dev: nullable device uint64[8]; while set, every
  * step / rollout kernel adds to it: [0] env-steps, [1] IK iterations executed, [2] constraint rows solved summed over

@@ -498,6 +498,148 @@ template <int ARM, int TASK> PIH_D bool apply_action(const SimParams& P, EnvStat
 #define PIH_MB_MTGT 30
 #define PIH_MB_GRASP_ANG 37
 
+// ---- three-warp small-batch kernels: exchange block in shared memory (one column per lane) and the named barriers
+// between the dynamics warp (warp 1) and the contacts warp (warp 2); barrier 0 (__syncthreads) is the hand-over of the
+// joint targets from the action warp (warp 0)
+#define PIH_WS_THREADS 96
+#define PIH_BAR_ABA 1     // dynamics -> contacts: the ABA factorisation is in X.ab
+#define PIH_BAR_FRONT 2   // contacts -> dynamics: contact summary / solved free-body island are in X.front, X.armc
+#define PIH_BAR_COLS 3    // contacts -> dynamics: the M^-1 columns [COLS_D, NB) are in X.cols
+template <int ARM> struct WsXch {
+  static constexpr int NB = ArmDims<ARM>::NB;
+  static constexpr int COLS_D = (NB + 1) / 2;   // M^-1 columns [0, COLS_D) are computed by the dynamics warp itself
+  float ab[NB][13][32];                         // per body: U (6), U / D (6), 1 / D
+  float cols[NB - COLS_D][NB][32];
+  float front[12][32];                          // contacts, pair mask, row-iterations, iterations, dv linear (3), dv angular (3)
+  int armc;                                     // some env of the warp has a contact that involves the arm
+};
+#define PIH_XF_N 0
+#define PIH_XF_PAIRS 1
+#define PIH_XF_ROWIT 2
+#define PIH_XF_IT 3
+#define PIH_XF_DVL 4
+#define PIH_XF_DVW 7
+// producer side: make the shared-memory stores visible, then arrive without waiting; consumer side: wait
+PIH_D void bar_arrive(int id) { __threadfence_block(); asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+PIH_D void bar_wait(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// Contacts warp of the small-batch kernels.  While the dynamics warp runs the articulated-body algorithm this warp does
+// the narrow phase and - when no env of the warp has a contact that involves the arm, the usual case - builds the rows
+// of the free-body island (free body vs static geometry) and solves it: that island depends neither on M^-1 nor on the
+// joint targets.  Otherwise it only raises X.armc and the dynamics warp takes its general path (collide + all rows).
+// Then it takes the ABA factorisation from shared memory and computes its share of the M^-1 columns.  Same operations in
+// the same order as the single-warp body (pih_step_body.inc), so every value is the oracle's, bit for bit.
+template <int ARM, int TASK> PIH_D void contacts_warp(const SimParams& P, const EnvState& S, const FK<ARM>& F, WsXch<ARM>& X, int lane) {
+  constexpr int nb = ArmDims<ARM>::NB;
+  const float dt = P.dt, idt = P.idt, im = P.fb_im;
+  m3 Rfb = quat_to_m3(S.pquat);
+  v3 fv = mk(S.pvel[0], S.pvel[1], fmaf(dt, (float)(-PIH_GRAVITY), S.pvel[2]));
+  v3 fw = mk(S.pang[0], S.pang[1], S.pang[2]);
+  {
+    v3 wb = mTv(Rfb, fw);
+    v3 Iw = mk(P.fb_idiag[0] * wb.x, P.fb_idiag[1] * wb.y, P.fb_idiag[2] * wb.z);
+    v3 g = vcross(wb, Iw);
+    v3 al = mk(-(g.x * P.fb_iinv[0]), -(g.y * P.fb_iinv[1]), -(g.z * P.fb_iinv[2]));
+    fw = clamp_norm(vaxpy(dt, mv(Rfb, al), fw));
+  }
+  m3 Iinv;
+  {
+    m3 Tm;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { Tm.m[r][0] = Rfb.m[r][0] * P.fb_iinv[0]; Tm.m[r][1] = Rfb.m[r][1] * P.fb_iinv[1]; Tm.m[r][2] = Rfb.m[r][2] * P.fb_iinv[2]; }
+    Iinv = mmulT(Tm, Rfb);
+  }
+  ContactSet CS;
+  collide<ARM, TASK>(P, S, F, Rfb, fsm_state_now<TASK>(S, false), CS);
+  int pairmask = 0;
+  bool arm_contacts = false;
+  for (int k = 0; k < CS.n; ++k) { pairmask |= CS.c[k].pair; arm_contacts = arm_contacts || (CS.c[k].arm_body >= 0); }
+  const bool w_armc = __any_sync(0xffffffffu, arm_contacts);
+  v3 dvl = mk(0.0f, 0.0f, 0.0f), dvw = dvl;
+  int st_rowit = 0, st_it = 0;
+  if (!w_armc) {
+    struct FbRow { v3 dir[3], jang[3], mang[3]; float dinv[3], diag[3], b[3], lam[3], mu; } rows[PIH_MAXC];
+    const v3 pfb = mk(S.ppos[0], S.ppos[1], S.ppos[2]);
+    for (int k = 0; k < CS.n; ++k) {
+      const Contact& c = CS.c[k];
+      FbRow& r = rows[k];
+      r.mu = c.mu;
+      r.dir[0] = c.n; plane_space(c.n, r.dir[1], r.dir[2]);
+      v3 rr = vsub(c.p, pfb);
+      for (int d = 0; d < 3; ++d) {
+        r.jang[d] = vcross(rr, r.dir[d]);
+        r.mang[d] = mv(Iinv, r.jang[d]);
+        const float diag = im + vdot(r.jang[d], r.mang[d]);
+        const float vrel = vdot(r.dir[d], fv) + vdot(r.jang[d], fw);
+        r.dinv[d] = 1.0f / diag;
+        r.diag[d] = diag;
+        float tv = 0.0f;
+        if (d == 0) tv = (c.dist > 0.0f) ? -(c.dist * idt) : -((float)PIH_ERP * c.dist * idt);
+        r.b[d] = (tv - vrel) * r.dinv[d];
+        r.lam[d] = 0.0f;
+      }
+    }
+    bool fb_on = true;
+    for (int it = 0; it < P.solver_iters; ++it) {
+      float res_f = 0.0f;
+      st_rowit += fb_on ? 3 * CS.n : 0; st_it += fb_on ? 1 : 0;
+      if (fb_on) {
+        for (int k = 0; k < CS.n; ++k) {
+          FbRow& r = rows[k];
+          float rel = vdot(r.dir[0], dvl) + vdot(r.jang[0], dvw);
+          float dl = fmaf(-rel, r.dinv[0], r.b[0]);
+          dl = fmaxf(dl, -r.lam[0]);
+          r.lam[0] += dl;
+          float rv = dl * r.diag[0];
+          res_f = fmaxf(res_f, rv * rv);
+          dvl = vaxpy(dl * im, r.dir[0], dvl);
+          dvw = vaxpy(dl, r.mang[0], dvw);
+        }
+        for (int k = 0; k < CS.n; ++k) {
+          FbRow& r = rows[k];
+          const float lim = r.mu * r.lam[0];
+#pragma unroll
+          for (int d = 1; d < 3; ++d) {
+            float rel = vdot(r.dir[d], dvl) + vdot(r.jang[d], dvw);
+            float dl = fmaf(-rel, r.dinv[d], r.b[d]);
+            dl = fminf(fmaxf(dl, -lim - r.lam[d]), lim - r.lam[d]);
+            r.lam[d] += dl;
+            float rv = dl * r.diag[d];
+            res_f = fmaxf(res_f, rv * rv);
+            dvl = vaxpy(dl * im, r.dir[d], dvl);
+            dvw = vaxpy(dl, r.mang[d], dvw);
+          }
+        }
+      }
+      if (res_f <= P.solver_residual) fb_on = false;
+      if (!__any_sync(0xffffffffu, fb_on)) break;
+    }
+  }
+  X.front[PIH_XF_N][lane] = __int_as_float(CS.n); X.front[PIH_XF_PAIRS][lane] = __int_as_float(pairmask);
+  X.front[PIH_XF_ROWIT][lane] = __int_as_float(st_rowit); X.front[PIH_XF_IT][lane] = __int_as_float(st_it);
+  X.front[PIH_XF_DVL][lane] = dvl.x; X.front[PIH_XF_DVL + 1][lane] = dvl.y; X.front[PIH_XF_DVL + 2][lane] = dvl.z;
+  X.front[PIH_XF_DVW][lane] = dvw.x; X.front[PIH_XF_DVW + 1][lane] = dvw.y; X.front[PIH_XF_DVW + 2][lane] = dvw.z;
+  if (lane == 0) X.armc = w_armc ? 1 : 0;
+  PIH_TICK(10);
+  bar_arrive(PIH_BAR_FRONT);
+  bar_wait(PIH_BAR_ABA);
+  ABA<ARM> AB;
+#pragma unroll
+  for (int i = 0; i < nb; ++i) {
+    AB.U[i].a = mk(X.ab[i][0][lane], X.ab[i][1][lane], X.ab[i][2][lane]); AB.U[i].l = mk(X.ab[i][3][lane], X.ab[i][4][lane], X.ab[i][5][lane]);
+    AB.UD[i].a = mk(X.ab[i][6][lane], X.ab[i][7][lane], X.ab[i][8][lane]); AB.UD[i].l = mk(X.ab[i][9][lane], X.ab[i][10][lane], X.ab[i][11][lane]);
+    AB.Dinv[i] = X.ab[i][12][lane];
+  }
+  for (int j = WsXch<ARM>::COLS_D; j < nb; ++j) {
+    float col[nb];
+    minv_column<ARM>(F, AB, j, col);
+#pragma unroll
+    for (int i = 0; i < nb; ++i) X.cols[j - WsXch<ARM>::COLS_D][i][lane] = col[i];
+  }
+  PIH_TICK(11);
+  bar_arrive(PIH_BAR_COLS);
+}
+
 // Everything of one env.step after apply_action: stepSimulation (ABA, M^-1, contacts, PGS, integration) and get_info.
 // The body lives in pih_step_body.inc and is instantiated twice: the classic single-warp order and the warp-specialised
 // order, in which the joint targets arrive from the sibling warp through the shared-memory mailbox `mb` at the one
@@ -509,10 +651,10 @@ __device__ __forceinline__ void step_back(const SimParams& P, EnvState& S, const
 #include "pih_step_body.inc"
 #undef PIH_STEP_WS
 }
-template <int ARM, int TASK>
+template <int ARM, int TASK, int NW>
 __device__ __forceinline__ void step_back_ws(const SimParams& P, EnvState& S, const FK<ARM>& F, float* qstar, float* kpc, float* mfc, bool fsm_done,
-                                             float (*mb)[32], int lane, bool commit, v3 off, unsigned gid, float (&obs)[5], float& reward,
-                                             unsigned char& done) {
+                                             float (*mb)[32], WsXch<ARM>& X, int lane, bool commit, v3 off, unsigned gid, float (&obs)[5],
+                                             float& reward, unsigned char& done) {
 #define PIH_STEP_WS 1
 #include "pih_step_body.inc"
 #undef PIH_STEP_WS

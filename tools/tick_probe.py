@@ -44,7 +44,7 @@ for t in range(steps):
     torch.cuda.synchronize()
     tot += ev0.elapsed_time(ev1)
     L.pih_debug_ticks(buf)
-    rows.append(list(buf)[:8])
+    rows.append(list(buf)[:9])
     L.pih_debug_cta_ns(cta)
     ctas.append(np.array(list(cta)[:2 * ((n + 31) // 32)], dtype=np.float64).reshape(-1, 2))
     if t in (180, 190):
@@ -72,7 +72,8 @@ print(f"warp1  FK+ABA+Minv+collide+rows    {us(2, 3):6.1f} us")
 print(f"warp1  barrier+motor/limit setup   {us(3, 4):6.1f} us")
 print(f"warp1  PGS                         {us(4, 5):6.1f} us")
 print(f"warp1  integrate+FK+get_info       {us(5, 7):6.1f} us")
-print(f"warp1  total (CTA 0)               {us(2, 7):6.1f} us")
+print(f"warp1  store state/obs/reward     {us(7, 8):6.1f} us")
+print(f"warp1  total (CTA 0)               {us(2, 8):6.1f} us")
 c = np.stack(ctas[50:])                      # [steps, ctas, 2] ns
 dur = (c[:, :, 1] - c[:, :, 0]) / 1e3
 span = (c[:, :, 1].max(1) - c[:, :, 0].min(1)) / 1e3
