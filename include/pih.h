@@ -109,20 +109,6 @@ int pih_step_host(pih_handle* h, const float* action_host, float* obs_host, floa
 int pih_host_bind(pih_handle* h, const void* host_ptr, uint64_t bytes);
 int pih_host_unbind(pih_handle* h, const void* host_ptr);
 
-/* Resident step server for the host-buffer path (NEW).  The reference's worker processes stay alive between steps and
- * are fed through queues (base_env_mp.py:40-51,75-87); the counterpart here is ONE resident launch of the three-warp step
- * kernel whose CTAs keep their envs' state on chip, wait for the host to publish a step in a page-locked control block,
- * run it, write (obs, reward, done) into the bound host buffers and publish completion, on which pih_server_step spins:
- * no kernel launch, no stream synchronisation and no state traffic per step.  Action-driven rigid-peg tasks, batches
- * that fit one resident wave (<= 2 CTAs of 32 envs per SM).  obs/reward/done_host and every action_host must be
- * page-locked and device-mapped (16-byte aligned).  The kernel retires itself after idle_timeout_ms without a step
- * (0 = 200 ms) and is restarted transparently by the next pih_server_step; any other entry point of the handle retires
- * it first (the state buffer is then current), and pih_server_step resumes it.  pih_server_step returns when the step's
- * outputs are in the host buffers.  Same bits as pih_step. */
-int pih_server_start(pih_handle* h, float* obs_host, float* reward_host, uint8_t* done_host, uint32_t idle_timeout_ms, void* stream);
-int pih_server_step(pih_handle* h, const float* action_host);
-int pih_server_stop(pih_handle* h);
-
 /* Execution statistics (NEW; measurement only).  stats_dev: nullable device uint64[8]; while set, every
  * step / rollout kernel adds to it: [0] env-steps, [1] IK iterations executed, [2] constraint rows solved summed over
  * solver iterations, [3] solver iterations, [4] contact points, [5] joint-limit rows, [6] envs force-reset by the

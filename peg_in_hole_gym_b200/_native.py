@@ -62,9 +62,6 @@ def lib():
     L.pih_rollout.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.pih_host_bind.argtypes = [vp, vp, C.c_uint64]
     L.pih_host_unbind.argtypes = [vp, vp]
-    L.pih_server_start.argtypes = [vp, vp, vp, vp, C.c_uint32, vp]
-    L.pih_server_step.argtypes = [vp, vp]
-    L.pih_server_stop.argtypes = [vp]
     L.pih_set_stats.argtypes = [vp, vp]
     L.pih_ik_targets.argtypes = [vp, vp, vp, vp]
     L.pih_ee_pose.argtypes = [vp, vp, vp, vp]
@@ -83,8 +80,7 @@ def lib():
     for name in ("pih_create", "pih_env_offset", "pih_reset", "pih_step", "pih_step_host", "pih_rollout",
                  "pih_ik_targets", "pih_ee_pose", "pih_measure_fp32_peak", "pih_action_dim", "pih_render", "pih_grasp_labels",
                  "pih_step_signal", "pih_peer_alloc", "pih_peer_open", "pih_peer_release", "pih_enable_peer", "pih_signal_flag", "pih_wait_flags",
-                 "pih_host_bind", "pih_host_unbind", "pih_set_stats", "pih_step_signal_wait", "pih_render_grasp",
-                 "pih_server_start", "pih_server_step", "pih_server_stop"):
+                 "pih_host_bind", "pih_host_unbind", "pih_set_stats", "pih_step_signal_wait", "pih_render_grasp"):
         getattr(L, name).restype = C.c_int
     if L.pih_abi_version() != 2:
         raise ImportError("libpih_b200.so ABI version mismatch")
@@ -96,8 +92,7 @@ EXPORTS = ["pih_abi_version", "pih_state_words", "pih_state_words_for", "pih_act
            "pih_last_error", "pih_env_offset", "pih_reset", "pih_step", "pih_step_host", "pih_rollout",
            "pih_ik_targets", "pih_ee_pose", "pih_render", "pih_grasp_labels", "pih_step_signal", "pih_peer_alloc", "pih_peer_open", "pih_peer_release",
            "pih_enable_peer", "pih_signal_flag",
-           "pih_wait_flags", "pih_measure_fp32_peak", "pih_host_bind", "pih_host_unbind", "pih_set_stats", "pih_step_signal_wait", "pih_render_grasp",
-           "pih_server_start", "pih_server_step", "pih_server_stop"]
+           "pih_wait_flags", "pih_measure_fp32_peak", "pih_host_bind", "pih_host_unbind", "pih_set_stats", "pih_step_signal_wait", "pih_render_grasp"]
 KERNEL_FAMILIES = {"auto": 0, "ws": 1, "fused": 2, "split": 3, "ws2": 4}
 PEG_MODELS = {"rigid": 0, "pipe": 1}      # pih_config.peg_model: one rigid segment / the reference's 25-link pipe.urdf chain
 

@@ -13,18 +13,14 @@ from . import _native as N
 
 class HostStepper:
     """Owner of one set of host buffers bound to a simulator (pih_host_bind / pih_host_unbind): the lifetime contract of
-    the zero-copy host path is this object's lifetime.  ``persistent=True`` serves the steps from the resident step
-    server (pih_server_*: no launch and no synchronisation call per step; buffers must be page-locked); any other call
-    on the simulator retires the server first (``sim.state`` is then current) and the next step resumes it."""
+    the zero-copy host path is this object's lifetime."""
 
-    def __init__(self, sim, action_nps, obs_np, reward_np, done_np, persistent=False, idle_timeout_ms=0):
+    def __init__(self, sim, action_nps, obs_np, reward_np, done_np):
         self._sim, self._keep = sim, (list(action_nps), obs_np, reward_np, done_np)
         self._a = [C.c_void_p(a.ctypes.data) for a in action_nps]
         self._o, self._r, self._d = (C.c_void_p(x.ctypes.data) for x in (obs_np, reward_np, done_np))
         self._fn, self._h, self._st = sim._L.pih_step_host, sim._h, C.c_void_p(sim._stream())
-        self._srv = sim._L.pih_server_step
         self._bound = []
-        self.persistent = False
         spans = sorted((a.ctypes.data, a.nbytes) for a in list(action_nps) + [obs_np, reward_np, done_np])
         merged = []
         for addr, nb in spans:                                  # views of one page-locked block bind as one range
@@ -35,23 +31,17 @@ class HostStepper:
         for addr, nb in merged:
             if sim._L.pih_host_bind(sim._h, addr, nb) == 0:      # pageable buffers stay unbound (queried per call)
                 self._bound.append(addr)
-        if persistent:
-            N.check(sim._L.pih_server_start(sim._h, self._o, self._r, self._d, int(idle_timeout_ms), self._st), sim._h, "pih_server_start")
-            self.persistent = True
 
     def __call__(self, i):
-        rc = self._srv(self._h, self._a[i]) if self.persistent else self._fn(self._h, self._a[i], self._o, self._r, self._d, self._st)
+        rc = self._fn(self._h, self._a[i], self._o, self._r, self._d, self._st)
         if rc:
-            N.check(rc, self._h, "pih_server_step" if self.persistent else "pih_step_host")
+            N.check(rc, self._h, "pih_step_host")
 
     def close(self):
-        if getattr(self._sim, "_h", None):
-            if self.persistent:
-                self._sim._L.pih_server_stop(self._sim._h)
+        if self._bound and getattr(self._sim, "_h", None):
             for p in self._bound:
                 self._sim._L.pih_host_unbind(self._sim._h, p)
         self._bound = []
-        self.persistent = False
 
     def __del__(self):
         try:

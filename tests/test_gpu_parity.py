@@ -279,41 +279,6 @@ def test_zero_copy_host_path_with_frozen_envs_and_fresh_buffers(family):
     _assert_state_equal(sim, orc)
 
 
-@pytest.mark.parametrize("arm,auto_reset", [("panda", True), ("panda", False), ("ur5", True)])
-def test_resident_step_server_matches_oracle_and_survives_interleaved_calls(arm, auto_reset):
-    """pih_server_*: ONE resident launch serves the host-buffer steps (state stays on chip between steps, the host
-    publishes each step in a page-locked control block and spins on the completion word).  Every step's outputs equal the
-    oracle's, with a different action buffer per step, frozen envs (no auto_reset), a partial last CTA, other entry points
-    in between (they retire the server; the next step resumes it) and after the kernel has retired itself on its idle
-    clock (10 ms here)."""
-    import time
-    from peg_in_hole_gym_b200.sim import HostStepper
-    n = 100
-    sim, orc = _pair(n, arm=arm, offset=(2.0, 3.0, 0.0), seed=23, max_steps=9, auto_reset=auto_reset)
-    sim.reset(); orc.reset()
-    adim = 4 if arm == "panda" else 6
-    acts = _random_actions(n, adim, 30, sim.env_offsets().numpy(), 8)
-    pas, pobs, prew, pdone = sim.pinned_host_buffers(4)
-    hs = HostStepper(sim, pas, pobs, prew, pdone, persistent=True, idle_timeout_ms=10)
-    for t, a in enumerate(acts):
-        pas[t % 4][...] = a
-        pobs[...] = -7.0; prew[...] = -7.0; pdone[...] = 9
-        hs(t % 4)
-        oc, rc, dc = orc.step(a)
-        assert np.array_equal(pobs, oc) and np.array_equal(prew, rc) and np.array_equal(pdone, dc), t
-        if t == 8:
-            sim.ee_pose()                        # sim.state is stale while the server runs: any other entry point retires it first
-            _assert_state_equal(sim, orc)
-        if t == 12:
-            time.sleep(0.05)                     # the kernel leaves on its idle clock; the next step restarts it
-        if t == 15 and not auto_reset:
-            sim.reset(); orc.reset()             # frozen batch: reset through the ordinary call, then carry on
-    hs.close()
-    _assert_state_equal(sim, orc)
-    sim.step(torch.from_numpy(acts[0]).cuda()); orc.step(acts[0])      # ordinary launches continue from the same state
-    _assert_state_equal(sim, orc)
-
-
 def test_grasp_label_images_match_oracle():
     """SURVEY 8f rank 3, second half: the label images of random_grasp (peg_in_hole.py:65-98) - CUDA == oracle, exactly,
     before the capture, after it, and for hand-set angles on a non-square image."""
