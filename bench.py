@@ -44,9 +44,12 @@ FLOPS_BULLET_DEFAULT = 2.2e5                       # I_ik=20, I_pgs=50, n=9, R=3
 # report null (profiles/README.md lists the captures they come from)
 NCU_CAPTURES = {
     ("pih::k_step_ws", "panda", "peg-in-hole", 4096): {
-        "traffic_bytes": 950272,             # dram__bytes_read.sum + dram__bytes_write.sum per launch
-        "executed_flops_per_env_step": 5.11e4,   # (2*FFMA + FMUL + FADD thread-instructions) per launch / 4096 envs
-        "source": "profiles/r01_kstep_ws_ncu_full_v3.csv"},
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch with the batch's state NOT in L2 (ncu default cache control):
+        # 1.05 MB read (852 KB of state + actions, the rest is code and constant tables), writes absorbed by L2
+        "traffic_bytes": 1054464,
+        # 2*FFMA + 4*FFMA2 + FMUL + FADD thread-instructions of the SASS page of the hot capture / 4096 envs (three warps: FK runs three times)
+        "executed_flops_per_env_step": 5.57e4,
+        "source": "profiles/r02_kstep_ws3_ncu_full_cold.csv (traffic), profiles/r02_kstep_ws3_ncu_full_hot.csv + r02_summary.md section 3 (FLOPs)"},
 }
 
 
@@ -225,7 +228,7 @@ def config5_sweep(args, rank, world, local, dev, reduce_max, barrier):
 def contact_rich_probe(n, local, torch, barrier):
     """The regime a trained policy lives in: the scripted grasp episode at n envs - engine steps with
     the peg held between the fingers (finger<->peg rows couple the arm and free-body islands) beside the contact-free
-    approach phase, microseconds per engine step of the rollout kernel."""
+    approach phase, microseconds per engine step (pih_rollout)."""
     from peg_in_hole_gym_b200.sim import BatchedSim
     sim = BatchedSim(n, task="peg-in-hole-scripted", sub_num=n, offset=OFFSET, seed=SEED, device=local)
     sim.reset()
@@ -421,7 +424,7 @@ def main():
     rows_mean = (9 if args.arm == "panda" else 6) + executed["limit_rows_mean"] + 3 * executed["contacts_mean"]
 
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # single-launch rollout (in-kernel Philox actions); first launch of the kernel is a warm-up (local-memory resize)
+    # one pih_rollout call (in-kernel Philox actions; small batches: K launches chained by programmatic dependent launch)
     sim.rollout(2, count=False)
     barrier()
     e0.record()
@@ -548,7 +551,7 @@ def main():
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "bytes_per_env_step": BYTES_PER_ENV_STEP, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"}},
             "cpu_baseline": cpu,
-            "extra": {"rollout_single_launch_value": total_envs * args.steps / (roll_ms * 1e-3),
+            "extra": {"rollout_call_value": total_envs * args.steps / (roll_ms * 1e-3),   # ONE pih_rollout call: K chained launches, actions from Philox in-kernel
                       "wall_s_timed_region": t_wall, "contact_rich": contact_rich, "flexible_pipe": pipe, "config5": config5},
             "clocks": clocks,
         }

@@ -213,7 +213,7 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOC
 
 
 // ---- warp-specialised variants for small batches (one warp per scheduler is the limit of thread-per-env latency):
-// a CTA of 64 threads owns 32 envs; warp 0 runs apply_action (FK -> vel_constraint -> 20 IK iterations) while warp 1
+// a CTA of 96 (64) threads owns 32 envs; warp 0 runs apply_action (FK -> vel_constraint -> 20 IK iterations) while warp 1
 // runs the target-independent half of stepSimulation (ABA, M^-1, narrow phase, contact rows); the joint targets cross
 // through a shared-memory mailbox at the motor rows.  Same arithmetic as k_step / k_rollout, bit for bit.  Every lane
 // executes the whole code (frozen / padding lanes compute on a copy and never commit) so that both warps reach the

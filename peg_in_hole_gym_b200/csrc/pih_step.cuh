@@ -630,11 +630,12 @@ template <int ARM, int TASK> PIH_D void contacts_warp(const SimParams& P, const 
     AB.UD[i].a = mk(X.ab[i][6][lane], X.ab[i][7][lane], X.ab[i][8][lane]); AB.UD[i].l = mk(X.ab[i][9][lane], X.ab[i][10][lane], X.ab[i][11][lane]);
     AB.Dinv[i] = X.ab[i][12][lane];
   }
-  for (int j = WsXch<ARM>::COLS_D; j < nb; ++j) {
+  constexpr int c0 = WsXch<ARM>::COLS_D;
+  for (int j = c0; j < nb; ++j) {
     float col[nb];
     minv_column<ARM>(F, AB, j, col);
 #pragma unroll
-    for (int i = 0; i < nb; ++i) X.cols[j - WsXch<ARM>::COLS_D][i][lane] = col[i];
+    for (int i = 0; i < nb; ++i) X.cols[j - c0][i][lane] = col[i];
   }
   PIH_TICK(11);
   bar_arrive(PIH_BAR_COLS);
