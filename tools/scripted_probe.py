@@ -9,7 +9,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from peg_in_hole_gym_b200.sim import BatchedSim  # noqa: E402
 
-for n in (4096, 16384, 65536):
+sizes = [int(a) for a in sys.argv[1:]] or [4096, 16384, 65536]
+for n in sizes:
     sim = BatchedSim(n, task="peg-in-hole-scripted", sub_num=n, offset=(2.0, 3.0, 0.0), seed=0, device=0)
     sim.reset()
     sim.rollout(50, count=False)
