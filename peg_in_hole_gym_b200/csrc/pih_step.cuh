@@ -38,15 +38,19 @@ struct ContactSet {
 
 // keep the PIH_MAXC deepest candidates; ties keep the earlier candidate.  The margin test is inlined at every
 // candidate site; the (rare) insertion is one out-of-line copy so that it does not bloat the instruction stream.
-static __device__ __noinline__ void contact_insert(ContactSet& S, const Contact& c) {
+// One copy per <arm, task, kernel family> (TAG): with a single out-of-line function shared by the kernels of every
+// instantiation ptxas gives it one calling convention for all of them, and the register allocation of the callers' hot
+// loops suffers (solver sweep 250 instead of 236 instructions as soon as a second <arm, task> was instantiated in the
+// same module).
+template <int TAG> static __device__ __noinline__ void contact_insert(ContactSet& S, const Contact& c) {
   if (S.n < PIH_MAXC) { S.c[S.n++] = c; return; }
   int w = 0;
   for (int i = 1; i < PIH_MAXC; ++i)
     if (S.c[i].dist > S.c[w].dist) w = i;
   if (c.dist < S.c[w].dist) S.c[w] = c;
 }
-PIH_D void contact_push(ContactSet& S, const Contact& c) {
-  if (c.dist < (float)PIH_CONTACT_MARGIN) contact_insert(S, c);
+template <int TAG> PIH_D void contact_push(ContactSet& S, const Contact& c) {
+  if (c.dist < (float)PIH_CONTACT_MARGIN) contact_insert<TAG>(S, c);
 }
 
 PIH_D float sd_rect(float da, float db, float sa, float sb, float& na, float& nb_) {
@@ -145,7 +149,8 @@ template <int TASK> PIH_D int fsm_state_now(const EnvState& S, bool advanced) {
 }
 PIH_D bool grasp_active(int task, int fsm_now) { return task == PIH_TASK_SCRIPTED && fsm_now >= PIH_FSM_GRASP_FIRST && fsm_now <= PIH_FSM_GRASP_LAST; }
 
-template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvState& S, const FK<ARM>& F, const m3& Rfb, int fsm_now, ContactSet& CS) {
+// KID: which kernel family the call is compiled into (0 classic, 2 / 3 small-batch kernels): see contact_insert
+template <int ARM, int TASK, int KID> PIH_D void collide(const SimParams& P, const EnvState& S, const FK<ARM>& F, const m3& Rfb, int fsm_now, ContactSet& CS) {
   const ArmTables& T = c_arm[ARM];
   CS.n = 0;
   v3 pfb = mk(S.ppos[0], S.ppos[1], S.ppos[2]);
@@ -158,7 +163,7 @@ template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvSta
     v3 pc = mv_add(Rfb, mk(0.0f, S.rand_y, 0.0f), pfb);
     c.pair = PIH_PAIR_GRASP; c.has_fb = 1; c.arm_body = ArmDims<ARM>::EE; c.p = pee; c.n = vsub(pc, pee);
     c.dist = -1e30f; c.mu = -1.0f;
-    contact_push(CS, c);
+    contact_push<ARM * 8 + TASK + 64 * KID>(CS, c);
   }
   const float mu_static = P.fb_mu * (float)PIH_MU_DEFAULT;
   // (1) free body vs table plane
@@ -178,7 +183,7 @@ template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvSta
           v3 pt = vaxpy(-P.fb_half[0], t, cc);
           c.pair = PIH_PAIR_PEG_TABLE; c.has_fb = 1; c.arm_body = -1; c.p = pt; c.n = mk(0.0f, 0.0f, 1.0f);
           c.dist = pt.z - (float)PIH_TABLE_Z; c.mu = mu_static;
-          contact_push(CS, c);
+          contact_push<ARM * 8 + TASK + 64 * KID>(CS, c);
         }
       } else {
         float sgn = (naz > 0.0f) ? -1.0f : 1.0f;
@@ -189,7 +194,7 @@ template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvSta
           v3 pt = vaxpy((k & 1) ? -P.fb_half[0] : P.fb_half[0], (k & 2) ? ez : ex, cc);
           c.pair = PIH_PAIR_PEG_TABLE; c.has_fb = 1; c.arm_body = -1; c.p = pt; c.n = mk(0.0f, 0.0f, 1.0f);
           c.dist = pt.z - (float)PIH_TABLE_Z; c.mu = mu_static;
-          contact_push(CS, c);
+          contact_push<ARM * 8 + TASK + 64 * KID>(CS, c);
         }
       }
     } else {
@@ -199,7 +204,7 @@ template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvSta
         v3 pt = mv_add(Rfb, pl, pfb);
         c.pair = PIH_PAIR_PEG_TABLE; c.has_fb = 1; c.arm_body = -1; c.p = pt; c.n = mk(0.0f, 0.0f, 1.0f);
         c.dist = pt.z - (float)PIH_TABLE_Z; c.mu = mu_static;
-        contact_push(CS, c);
+        contact_push<ARM * 8 + TASK + 64 * KID>(CS, c);
       }
     }
   }
@@ -214,7 +219,7 @@ template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvSta
         v3 pt = mv_add(Rfb, pl, pfb);
         float d = hole_sdf(pt, nn);
         c.pair = PIH_PAIR_PEG_HOLE; c.has_fb = 1; c.arm_body = -1; c.p = pt; c.n = nn; c.dist = d; c.mu = mu_static;
-        contact_push(CS, c);
+        contact_push<ARM * 8 + TASK + 64 * KID>(CS, c);
       }
       for (int k = 0; k < 32; ++k) {
         float rr = (k < 16) ? (float)PIH_HOLE_RIN : (float)PIH_HOLE_ROUT;
@@ -225,7 +230,7 @@ template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvSta
         v3 nn;
         float d = fb_sdf<TASK>(P, Rfb, pfb, pt, nn);
         c.pair = PIH_PAIR_PEG_HOLE; c.has_fb = 1; c.arm_body = -1; c.p = pt; c.n = mk(-nn.x, -nn.y, -nn.z); c.dist = d; c.mu = mu_static;
-        contact_push(CS, c);
+        contact_push<ARM * 8 + TASK + 64 * KID>(CS, c);
       }
     }
   }
@@ -252,7 +257,7 @@ template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvSta
       v3 nn = mv(Rb, nl);
       c.pair = b ? PIH_PAIR_PEG_FINGER2 : PIH_PAIR_PEG_FINGER1; c.has_fb = 1; c.arm_body = body;
       c.p = vaxpy(-rad, nn, pt); c.n = nn; c.dist = d - rad; c.mu = P.fb_mu * (float)PIH_MU_FINGER;
-      contact_push(CS, c);
+      contact_push<ARM * 8 + TASK + 64 * KID>(CS, c);
     }
   }
   // (3b) free body vs arm collision spheres (hand, wrist, forearm); finger-tip spheres are covered by the boxes of (3)
@@ -269,7 +274,7 @@ template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvSta
         c.pair = PIH_PAIR_FB_ARM; c.has_fb = 1; c.arm_body = body;
         c.n = mk(-nn.x, -nn.y, -nn.z);
         c.p = vaxpy(-T.sph_r[s], nn, cw); c.dist = d - T.sph_r[s]; c.mu = P.fb_mu * (float)PIH_MU_DEFAULT;
-        contact_push(CS, c);
+        contact_push<ARM * 8 + TASK + 64 * KID>(CS, c);
       }
     }
   });
@@ -281,7 +286,7 @@ template <int ARM, int TASK> PIH_D void collide(const SimParams& P, const EnvSta
     c.pair = PIH_PAIR_ARM_TABLE; c.has_fb = 0; c.arm_body = body; c.n = mk(0.0f, 0.0f, 1.0f);
     c.p = mk(cw.x, cw.y, cw.z - T.sph_r[s]);
     c.dist = cw.z - T.sph_r[s] - (float)PIH_TABLE_Z; c.mu = (float)PIH_MU_DEFAULT * (float)PIH_MU_DEFAULT;
-    contact_push(CS, c);
+    contact_push<ARM * 8 + TASK + 64 * KID>(CS, c);
   }
 }
 
@@ -550,7 +555,7 @@ template <int ARM, int TASK> PIH_D void contacts_warp(const SimParams& P, const 
     Iinv = mmulT(Tm, Rfb);
   }
   ContactSet CS;
-  collide<ARM, TASK>(P, S, F, Rfb, fsm_state_now<TASK>(S, false), CS);
+  collide<ARM, TASK, 3>(P, S, F, Rfb, fsm_state_now<TASK>(S, false), CS);
   int pairmask = 0;
   bool arm_contacts = false;
   for (int k = 0; k < CS.n; ++k) { pairmask |= CS.c[k].pair; arm_contacts = arm_contacts || (CS.c[k].arm_body >= 0); }
