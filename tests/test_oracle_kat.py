@@ -124,6 +124,54 @@ def test_ik_fixed_point_and_convergence(arm, name):
 
 
 @pytest.mark.parametrize("arm,name", [(PANDA, "PANDA"), (UR5, "UR5")])
+def test_ik_matches_independent_damped_least_squares(arm, name):
+    """The IK restated independently (numpy + scipy rotations, geometric Jacobian from the independent FK of
+    tests/model_tables.py; shares no code with the oracle): dtheta = J^T (J J^T + lambda^2 I)^-1 e with lambda = 0.6,
+    e = [p* - p ; rotation vector of R* R^T], largest |dtheta| clamped to 45 degrees, a fixed number of iterations
+    seeded at the current joints - the algorithm DESIGN.md section 2.3 states.  The double oracle follows it to 1e-9 rad
+    after 1, 5 and 20 iterations, for small and for out-of-reach steps (where the clamp is active)."""
+    from scipy.spatial.transform import Rotation as Rot
+    A = Arm(name)
+    rng = np.random.default_rng(12)
+
+    def ik_np(q0, p_t, R_t, iters):
+        q = q0.copy()
+        for _ in range(iters):
+            Rw, pw = A.fk(q)
+            pe, Re = A.ee(q)
+            e = np.concatenate([p_t - pe, Rot.from_matrix(R_t @ Re.T).as_rotvec()])
+            if e @ e < 1e-8:
+                break
+            J = np.zeros((6, A.narm))
+            for j in range(A.narm):
+                z = Rw[j][:, 2]
+                J[:3, j], J[3:, j] = np.cross(z, pe - pw[j]), z
+            d = J.T @ np.linalg.solve(J @ J.T + 0.36 * np.eye(6), e)
+            m = np.abs(d).max()
+            if m > np.pi / 4:
+                d *= (np.pi / 4) / m
+            q[:A.narm] += d
+        return q[:A.narm]
+
+    for trial in range(12):
+        q = rng.uniform(-1.0, 1.0, A.nb)
+        if arm == PANDA:
+            q[3] = -1.5 + 0.5 * rng.uniform(-1, 1)
+            q[7:] = 0.0
+        scale = 0.05 if trial < 6 else 0.8            # second half: far targets, the 45 degree clamp engages
+        q2 = q.copy()
+        q2[:A.narm] += rng.uniform(-scale, scale, A.narm)
+        p_t, R_t = A.ee(q2)
+        if trial >= 9:
+            p_t = p_t + rng.uniform(-1.0, 1.0, 3)      # out of reach
+        quat = Rot.from_matrix(R_t).as_quat()
+        for iters in (1, 5, 20):
+            want = ik_np(q, p_t, R_t, iters)
+            got = ol.ik(arm, q, p_t, quat, iters, True)
+            assert np.allclose(got, want, atol=1e-9), (trial, iters, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("arm,name", [(PANDA, "PANDA"), (UR5, "UR5")])
 def test_aba_and_minv_match_lagrangian_model(arm, name):
     A = Arm(name)
     rng = np.random.default_rng(3)
