@@ -574,8 +574,9 @@ def test_randomised_states_fuzz_bit_exact(arm, task, fly):
 @pytest.mark.parametrize("arm,task", [("panda", "peg-in-hole"), ("ur5", "peg-in-hole"), ("panda", "random-fly"),
                                       ("panda", "peg-in-hole-scripted")])
 def test_all_kernel_families_agree_with_the_oracle(arm, task):
-    """Kernel families that compute one env.step: the warp-specialised small-batch kernels (k_step_ws / k_rollout_ws) with
-    three warps per 32 envs (action / dynamics / contacts; "ws") and with two ("ws2", batches of 9473..18944 envs),
+    """Kernel families that compute one env.step: the warp-specialised small-batch kernel k_step_ws with three warps per
+    32 envs (action / dynamics / contacts; "ws") and with two ("ws2", batches of 9473..18944 envs; pih_rollout on both =
+    chained launches of the same kernel with in-kernel actions),
     the fused thread-per-env kernels (k_step / k_rollout) and the split pair k_apply_action + k_step_dyn that batches
     >= 49152 envs (BASELINE config 5) run.  pih_config.kernel_family forces each of them at a test-sized batch; all
     must give the oracle's bits, for pih_step with EXTERNAL actions and for pih_rollout.  (The scripted task has no
