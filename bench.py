@@ -129,12 +129,35 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def bench_config(args, world, gather):
+    """The `config` object of the JSON line - ONE function for both arms, so that the reference arm (--impl reference)
+    reports exactly the config of the arm it is compared with."""
+    n = args.envs_per_gpu
+    adim = 4 if args.arm == "panda" else 6
+    dt_sim = 1.0 / 120.0 if args.task == "random-fly" else 1.0 / 240.0
+    bytes_per_batch = n * (192 + adim * 4 + 25)
+    nb_batches = 1 if args.l2 == "flush" else max(2, -(-160_000_000 // bytes_per_batch))
+    stride = coprime_stride(nb_batches)
+    return {"workload": f"{args.task} {args.arm}, {n} sub-envs per GPU (BASELINE config 2), dt 1/{round(1 / dt_sim)}, "
+                        f"{MAX_STEPS}-step episodes + auto-reset, U[-1,1]^{adim} actions centred on env origin, offset {list(OFFSET)}",
+            "envs_per_gpu": n, "total_envs": n * world, "solver_iters": 50, "ik_iters": 20,
+            "l2": (f"inputs larger than L2: {nb_batches} independent {n}-env batches ({nb_batches * bytes_per_batch / 1e6:.0f} MB of state+actions+outputs), "
+                   f"batch b pre-rolled to episode phase b*{MAX_STEPS}/{nb_batches} and visited with stride {stride} (coprime), so every window of "
+                   "consecutive steps covers the phases evenly; K launches inside one CUDA-event pair"
+                   if args.l2 == "rotate" else "flushed between timed steps (256 MiB memset); per-step CUDA events summed"),
+            "gather_to_rank0": gather if world > 1 else False, "peer_wait": args.peer_wait if gather == "peer" else None,
+            "parallelism": f"env-sharded x{world}, " + ("no data-path collective" if gather == "none" else
+                                                         ("rows stored into rank 0's learner buffer by the step kernel over NVLink peer memory (no collective)"
+                                                          if gather == "peer" else "pack + NCCL gather to rank 0 every step"))}
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation is PyBullet (not installable here) -> oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = host_threads()
+    ref_gather = (args.gather or "peer") if args.gpus > 1 else "none"   # (as the b200 arm resolves it)
     # same config as the b200 arm: 4096 panda sub-envs; one bench "step" = one env.step of that batch, run in blocks
     n = args.envs_per_gpu
     block = 25
@@ -147,8 +170,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "peg-in-hole env-steps/sec", "value": rate, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / t_steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "peg-in-hole panda, dt 1/240, 200-step episodes, U[-1,1]^4 actions (config 2 shape)",
-                       "envs_per_gpu": n, "total_envs": n, "note": "PyBullet not installable (no wheel/network): CPU restatement (oracle/), not PyBullet"},
+            # the config of the arm this line is compared with (same function); what ran here: the CPU restatement of that
+            # workload on rank 0's host threads, a bounded sample of it per step
+            "config": bench_config(args, max(args.gpus, 1), ref_gather),
+            "note": "PyBullet not installable (no wheel/network): CPU restatement (oracle/), not PyBullet",
             "cpu_baseline": {"value": rate, "unit": "env-steps/s", "cores": threads, "kind": "port",
                              "sample": f"{n} envs x {t_steps} steps, {threads} host threads"},
             "e2e": {"value": rate, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -518,17 +543,7 @@ def main():
             "metric": "peg-in-hole env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.task} {args.arm}, {n} sub-envs per GPU (BASELINE config 2), dt 1/{round(1 / dt_sim)}, "
-                                   f"{MAX_STEPS}-step episodes + auto-reset, U[-1,1]^{adim} actions centred on env origin, offset {list(OFFSET)}",
-                       "envs_per_gpu": n, "total_envs": total_envs, "solver_iters": 50, "ik_iters": 20,
-                       "l2": (f"inputs larger than L2: {nb_batches} independent {n}-env batches ({nb_batches * bytes_per_batch / 1e6:.0f} MB of state+actions+outputs), "
-                              f"batch b pre-rolled to episode phase b*{MAX_STEPS}/{nb_batches} and visited with stride {stride} (coprime), so every window of "
-                              "consecutive steps covers the phases evenly; K launches inside one CUDA-event pair"
-                              if args.l2 == "rotate" else "flushed between timed steps (256 MiB memset); per-step CUDA events summed"),
-                       "gather_to_rank0": gather if world > 1 else False, "peer_wait": args.peer_wait if gather == "peer" else None,
-                       "parallelism": f"env-sharded x{world}, " + ("no data-path collective" if gather == "none" else
-                                                                    ("rows stored into rank 0's learner buffer by the step kernel over NVLink peer memory (no collective)"
-                                                                     if gather == "peer" else "pack + NCCL gather to rank 0 every step"))},
+            "config": bench_config(args, world, gather),
             "e2e": {"value": total_envs * e2e_steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n * adim * 4,
                     "d2h_bytes_per_step": n * (20 + 4 + 1), "steps": e2e_steps,
                     "staged_copy_value": total_envs * e2e_steps / staged_s, "timing": "wall clock per step: pih_step_host on page-locked host buffers = one launch whose SMs read that step's actions from host memory and write obs|reward|done back to host memory over PCIe (zero-copy), stream sync, host reads the result; a fresh i.i.d. host action batch every step; staged_copy_value = the same loop with explicit cudaMemcpyAsync H2D + step + D2H"},
