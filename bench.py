@@ -400,7 +400,8 @@ def main():
         if peer is not None:
             # outputs go straight into rank 0's learner buffer, then the flag; rank 0's kernel first waits for the
             # previous step's rows of every rank (the consumer's wait, folded into its next launch)
-            peer.step(a, sm, wait_prev=(rank == 0 and args.peer_wait == "folded"))
+            # (folded mode: deferred publication - the step stores its rows, the next launch announces them)
+            peer.step(a, sm, wait_prev=(rank == 0 and args.peer_wait == "folded"), deferred=(args.peer_wait == "folded"))
             if rank == 0 and args.peer_wait == "kernel":
                 peer.wait()
         else:
@@ -427,6 +428,8 @@ def main():
         t_wall0 = time.perf_counter()
         dev_ms = timed_steps(lambda i: one(args.warmup + i), args.steps, barrier, torch)
         t_wall = time.perf_counter() - t_wall0
+    if peer is not None:
+        peer.flush()      # deferred publication: every rank announces its last step's rows
     if peer is not None and rank == 0:
         peer.wait()       # the last step's rows
         peer.check()      # no device-side wait may have timed out

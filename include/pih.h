@@ -163,6 +163,17 @@ int pih_step_signal(pih_handle* h, const float* action_dev, float* obs_dev, floa
 int pih_step_signal_wait(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint32_t* flag_dev,
                          uint32_t flag_value, const uint32_t* wait_flags_dev, int32_t wait_count, uint32_t wait_value, uint32_t timeout_ms,
                          uint32_t* timed_out_dev, void* stream);
+
+/* Deferred publication of the same gather (NEW).  pih_step_signal makes every CTA of the step fence at system scope before
+ * it leaves (its rows must have landed in the learner's memory before the flag may follow): ~6 us per step at 4096 envs.
+ * Here the step stores its rows and leaves; the NEXT launch of the stream announces them: at its start (the previous
+ * launch has completed by stream order) one thread fences once and stores prev_value into flag_dev.  So a loop of
+ * pih_step_publish_prev(..., prev_value = t - 1, ...) for t = 1, 2, ... delivers the flags one launch later and costs
+ * the steps nothing; the rows of the last step are announced by pih_signal_flag.  wait_flags_dev (nullable) as in
+ * pih_step_signal_wait: the learner's rank waits for wait_count flags >= wait_value before it touches anything. */
+int pih_step_publish_prev(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint32_t* flag_dev,
+                          uint32_t prev_value, const uint32_t* wait_flags_dev, int32_t wait_count, uint32_t wait_value, uint32_t timeout_ms,
+                          uint32_t* timed_out_dev, void* stream);
 int pih_peer_alloc(int32_t device, uint64_t bytes, void** ptr_out, uint8_t handle_out[64]);  /* owner: zeroed buffer + its IPC handle */
 int pih_peer_open(int32_t device, const uint8_t handle[64], void** ptr_out);   /* other rank: map it on ITS device (peer memory) */
 int pih_peer_release(void* ptr, int32_t is_owner);

@@ -70,6 +70,7 @@ def lib():
     L.pih_render_grasp.argtypes = [vp, i32, i32, vp, vp]
     L.pih_step_signal.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint32, vp]
     L.pih_step_signal_wait.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint32, vp, i32, C.c_uint32, C.c_uint32, vp, vp]
+    L.pih_step_publish_prev.argtypes = [vp, vp, vp, vp, vp, vp, C.c_uint32, vp, i32, C.c_uint32, C.c_uint32, vp, vp]
     L.pih_peer_alloc.argtypes = [i32, C.c_uint64, C.POINTER(vp), C.c_char_p]
     L.pih_peer_open.argtypes = [i32, C.c_char_p, C.POINTER(vp)]
     L.pih_peer_release.argtypes = [vp, i32]
@@ -80,7 +81,7 @@ def lib():
     for name in ("pih_create", "pih_env_offset", "pih_reset", "pih_step", "pih_step_host", "pih_rollout",
                  "pih_ik_targets", "pih_ee_pose", "pih_measure_fp32_peak", "pih_action_dim", "pih_render", "pih_grasp_labels",
                  "pih_step_signal", "pih_peer_alloc", "pih_peer_open", "pih_peer_release", "pih_enable_peer", "pih_signal_flag", "pih_wait_flags",
-                 "pih_host_bind", "pih_host_unbind", "pih_set_stats", "pih_step_signal_wait", "pih_render_grasp"):
+                 "pih_host_bind", "pih_host_unbind", "pih_set_stats", "pih_step_signal_wait", "pih_render_grasp", "pih_step_publish_prev"):
         getattr(L, name).restype = C.c_int
     if L.pih_abi_version() != 2:
         raise ImportError("libpih_b200.so ABI version mismatch")
@@ -92,7 +93,7 @@ EXPORTS = ["pih_abi_version", "pih_state_words", "pih_state_words_for", "pih_act
            "pih_last_error", "pih_env_offset", "pih_reset", "pih_step", "pih_step_host", "pih_rollout",
            "pih_ik_targets", "pih_ee_pose", "pih_render", "pih_grasp_labels", "pih_step_signal", "pih_peer_alloc", "pih_peer_open", "pih_peer_release",
            "pih_enable_peer", "pih_signal_flag",
-           "pih_wait_flags", "pih_measure_fp32_peak", "pih_host_bind", "pih_host_unbind", "pih_set_stats", "pih_step_signal_wait", "pih_render_grasp"]
+           "pih_wait_flags", "pih_measure_fp32_peak", "pih_host_bind", "pih_host_unbind", "pih_set_stats", "pih_step_signal_wait", "pih_render_grasp", "pih_step_publish_prev"]
 KERNEL_FAMILIES = {"auto": 0, "ws": 1, "fused": 2, "split": 3, "ws2": 4}
 PEG_MODELS = {"rigid": 0, "pipe": 1}      # pih_config.peg_model: one rigid segment / the reference's 25-link pipe.urdf chain
 

@@ -242,6 +242,8 @@ template <int ARM, int TASK> PIH_D void mailbox_put(float (*mb)[32], int lane, c
 struct StepSignal {
   unsigned* flag; unsigned value; unsigned* cta_counter;
   const unsigned* wait_flags; int wait_count; unsigned wait_value; unsigned long long timeout_ns; unsigned* timed_out;
+  // cta_counter == NULL with a flag: deferred publication (pih_step_publish_prev) - this launch announces `value` at its
+  // START (everything the stream did before it, i.e. the previous step's rows, has been delivered) and nothing at its end
 };
 // bounded spin of one thread on one flag word (steps count up, so >=); records the index of a flag that never came
 // acquire load at system scope: what the flag's writer (a kernel on another GPU) released is visible after it - without a
@@ -271,6 +273,13 @@ template <int ARM, int TASK, int NW> __global__ void __launch_bounds__(NW * 32, 
   const int e = blockIdx.x * 32 + lane;
   const int ec = e < P.n ? e : P.n - 1;
   pdl_wait();
+  if (sig.flag && !sig.cta_counter && blockIdx.x == 0 && threadIdx.x == (NW - 1) * 32) {
+    // The previous launch of this stream (the step that wrote the rows being announced) has completed - that is what
+    // pdl_wait / stream order guarantee - so one system-scope fence orders all of its stores before the flag
+    // (cumulativity), and no CTA of any step pays for a fence on its way out.  Lane 0 of the warp with the most slack.
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned*>(sig.flag) = sig.value;
+  }
   if (sig.wait_flags) {
     // learner rank: the rows of the previous step of every rank must have landed before this step's rows may follow
     // (the consumer's wait, folded into its next launch instead of a kernel of its own)
@@ -345,7 +354,7 @@ template <int ARM, int TASK, int NW> __global__ void __launch_bounds__(NW * 32, 
     if (reward) reward[e] = r;
     if (done) done[e] = d;
   }
-  if (sig.flag) {
+  if (sig.flag && sig.cta_counter) {
     // Fused gather epilogue: the output pointers may be peer mappings of a learner buffer on another
     // GPU.  Every CTA makes its rows visible system-wide and counts itself; the last one publishes the step number in
     // this rank's flag word (and re-arms the counter), so no separate signalling launch follows the step.
@@ -744,17 +753,35 @@ int pih_step_signal_wait(pih_handle* h, const float* action_dev, float* obs_dev,
   return step_impl(h, action_dev, obs_dev, reward_dev, done_dev, sig, stream);
 }
 
+int pih_step_publish_prev(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, uint32_t* flag_dev,
+                          uint32_t prev_value, const uint32_t* wait_flags_dev, int32_t wait_count, uint32_t wait_value, uint32_t timeout_ms,
+                          uint32_t* timed_out_dev, void* stream) {
+  if (!flag_dev || (wait_flags_dev && (!timed_out_dev || wait_count <= 0 || wait_count > 64))) return PIH_ERR_INVALID;
+  StepSignal sig = {};
+  sig.flag = flag_dev; sig.value = prev_value; sig.wait_count = -1;   // (-1: deferred; step_impl keeps cta_counter NULL)
+  if (wait_flags_dev) {
+    sig.wait_flags = wait_flags_dev; sig.wait_count = -wait_count - 1; sig.wait_value = wait_value;
+    sig.timeout_ns = (unsigned long long)timeout_ms * 1000000ull; sig.timed_out = timed_out_dev;
+  }
+  return step_impl(h, action_dev, obs_dev, reward_dev, done_dev, sig, stream);
+}
+
 static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev, StepSignal sig, void* stream) {
   if (!h || !action_dev) return PIH_ERR_INVALID;
   if (!h->was_reset) return fail(h, PIH_ERR_STATE, "step() before reset()", cudaSuccess);
   if ((uintptr_t)action_dev & (h->P.arm == PIH_ARM_PANDA ? 15 : 7)) return fail(h, PIH_ERR_INVALID, "action rows must be 16-byte (Box(4)) / 8-byte (Box(6)) aligned", cudaSuccess);
   USE_DEVICE(h);
-  sig.cta_counter = h->d_cta_counter;
-  uint32_t* const flag_dev = sig.flag;
+  const bool deferred = sig.wait_count < 0;        // pih_step_publish_prev: wait_count arrives as -(count) - 1
+  if (deferred) sig.wait_count = -sig.wait_count - 1;
+  sig.cta_counter = deferred ? nullptr : h->d_cta_counter;
+  uint32_t* const pub_flag = deferred ? sig.flag : nullptr;      // announced at the START of this call
+  uint32_t* const flag_dev = deferred ? nullptr : sig.flag;      // announced at its end
   const uint32_t flag_value = sig.value;
   // signalled step of a large batch: the kernels write a local block, one copy kernel delivers it and publishes the flag
   float* const out_obs = obs_dev; float* const out_rew = reward_dev; uint8_t* const out_done = done_dev;
-  const bool staged_rows = flag_dev && !h->ws && obs_dev && reward_dev && done_dev;
+  const bool staged_rows = (flag_dev || pub_flag) && !h->ws && obs_dev && reward_dev && done_dev;
+  // deferred publication outside the small-batch kernels: a one-thread launch in front of the step
+  if (pub_flag && (h->pipe || !h->ws)) k_signal_flag<<<1, 1, 0, (cudaStream_t)stream>>>(pub_flag, flag_value);
   if (staged_rows) {
     const size_t n = (size_t)h->P.n;
     if (!h->d_stage && cudaMalloc(&h->d_stage, n * 24 + ((n + 15) & ~(size_t)15)) != cudaSuccess)
@@ -794,7 +821,7 @@ static int step_impl(pih_handle* h, const float* action_dev, float* obs_dev, flo
       if (cc == cudaSuccess) cc = cudaMemcpyAsync(out_done, done_dev, n, cudaMemcpyDeviceToDevice, st);
     }
     if (cc != cudaSuccess) return fail(h, PIH_ERR_CUDA, "row copy to the learner buffer", cc);
-    k_signal_flag<<<1, 1, 0, st>>>(flag_dev, flag_value);
+    if (flag_dev) k_signal_flag<<<1, 1, 0, st>>>(flag_dev, flag_value);
   }
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) return fail(h, PIH_ERR_CUDA, "k_step launch", ce);

@@ -47,6 +47,23 @@ def main():
                 ok = ok and torch.equal(rows[r][0], refs[r].obs) and torch.equal(rows[r][1], refs[r].reward) and torch.equal(rows[r][2], refs[r].done)
         torch.cuda.synchronize()
         dist.barrier()          # lockstep only because rank 0 re-uses the buffer slice every step in this test
+    # deferred publication: the steps only store their rows, every rank's next launch (or flush) announces them
+    for t in range(25, 33):
+        acts = [torch.from_numpy(np.random.default_rng(1000 * t + r).uniform(-1, 1, (counts[r], 4)).astype(np.float32)).cuda() for r in range(ws)]
+        peer.step(acts[rank] + my_off, deferred=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        peer.flush()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            rows = peer.wait()
+            for r in range(ws):
+                refs[r].step(acts[r] + offs[r])
+                torch.cuda.synchronize()
+                ok = ok and torch.equal(rows[r][0], refs[r].obs) and torch.equal(rows[r][1], refs[r].reward) and torch.equal(rows[r][2], refs[r].done)
+        torch.cuda.synchronize()
+        dist.barrier()
     if rank == 0:
         peer.check()
         print("PEER_GATHER_OK" if ok else "PEER_GATHER_MISMATCH", flush=True)

@@ -338,6 +338,27 @@ def test_peer_write_gather_on_one_gpu_matches_plain_outputs():
             assert torch.equal(rows[r][0], refs[r].obs) and torch.equal(rows[r][1], refs[r].reward)
             assert torch.equal(rows[r][2], refs[r].done)
     members[0].check()
+    # deferred publication (pih_step_publish_prev): a step only stores its rows, the NEXT launch announces them with one
+    # fence at its start; the owner's folded wait looks for the previous step's flags, flush() announces the last step
+    flags = buf[members[0].flag_off:members[0].flag_off + 8].view(torch.int32)
+    for t in range(12):
+        acts = [torch.from_numpy(rng.uniform(-1, 1, (n, 4)).astype(np.float32)).cuda() + torch.cat(
+            [sims[r].env_offsets().cuda(), torch.zeros(n, 1, device="cuda")], 1) for r in range(2)]
+        members[1].step(acts[1], deferred=True)
+        members[0].step_no = members[1].step_no - 1
+        members[0].step(acts[0], deferred=True, wait_prev=True)
+        torch.cuda.synchronize()
+        assert flags.tolist() == [members[0].step_no - 1] * 2, (t, flags.tolist())      # announced so far: the previous step
+        for r in range(2):
+            refs[r].step(acts[r])
+    for m in members:
+        m.flush()
+    rows = members[0].wait()
+    torch.cuda.synchronize()
+    assert flags.tolist() == [members[0].step_no] * 2
+    for r in range(2):
+        assert torch.equal(rows[r][0], refs[r].obs) and torch.equal(rows[r][1], refs[r].reward) and torch.equal(rows[r][2], refs[r].done)
+    members[0].check()
     # a flag that never arrives: the bounded wait gives up and reports which one
     members[0].step_no += 1
     members[0].wait(timeout_ms=20)
