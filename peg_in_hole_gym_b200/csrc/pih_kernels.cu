@@ -212,16 +212,21 @@ template <int ARM, int TASK> __global__ void __launch_bounds__(128, PIH_MIN_BLOC
 }
 
 
-// ---- warp-specialised variants for small batches (one warp per scheduler is the limit of thread-per-env latency):
-// a CTA of 96 (64) threads owns 32 envs; warp 0 runs apply_action (FK -> vel_constraint -> 20 IK iterations) while warp 1
-// runs the target-independent half of stepSimulation (ABA, M^-1, narrow phase, contact rows); the joint targets cross
-// through a shared-memory mailbox at the motor rows.  Same arithmetic as k_step / k_rollout, bit for bit.  Every lane
-// executes the whole code (frozen / padding lanes compute on a copy and never commit) so that both warps reach the
-// barriers converged.
+// ---- warp-specialised kernel for small batches (4096 envs are 128 groups of 32: the step is as long as ONE warp's
+// instruction stream, and an SM sub-partition issues an FP32 instruction every second cycle - DESIGN.md 5c).  A CTA owns
+// 32 envs and spreads one step's independent recurrences over NW warps, one per sub-partition:
+//   warp 0  apply_action: FK -> vel_constraint -> 20 branch-free IK iterations; targets into the mailbox `mb`
+//   warp 1  dynamics: FK, ABA (factorisation published in X.ab), its share of the M^-1 columns, motor / limit rows, and
+//           after the hand-over of the targets (barrier 0) the solver loop, integration, get_info, stores
+//   warp 2  (NW == 3) contacts: FK, narrow phase, rows and solve of the free-body island, the other M^-1 columns
+// Same arithmetic as k_step / k_rollout, bit for bit.  Every lane executes the whole code (frozen / padding lanes
+// compute on a copy and never commit) so that the warps reach their barriers converged.  pih_rollout on these batches is
+// K launches of this kernel with action == NULL (actions drawn in-kernel): a kernel that loops over the steps is
+// compiled worse (profiles/r02_summary.md 2d).
 // Programmatic dependent launch.  The small-batch kernels are launched with programmatic stream serialisation: once
 // every CTA of step N has passed its solver loop (pdl_trigger, in pih_step_body.inc) the CTAs of step N+1 may be
 // scheduled; they wait here until step N has completed and flushed its memory.  This overlaps the launch latency of
-// the back-to-back ~45 us kernels of a rollout with the tail of the previous step.  With any other predecessor in the
+// the back-to-back ~40 us kernels of a rollout with the tail of the previous step.  With any other predecessor in the
 // stream the wait returns only after that predecessor has finished (normal stream order).
 PIH_D void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

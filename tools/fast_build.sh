@@ -8,5 +8,5 @@ mkdir -p "$here/_build"
 out="$here/_build/libpih_$1.so"; shift
 cd "$here/../peg_in_hole_gym_b200/csrc"
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -std=c++17 -Xcompiler -fPIC -shared -diag-suppress 177 \
-  -split-compile 0 -DPIH_FAST_BUILD "$@" -o "$out" pih_kernels.cu build/pih_pipe.o
+  -split-compile 8 -DPIH_FAST_BUILD "$@" -o "$out" pih_kernels.cu build/pih_pipe.o
 echo "$out"
