@@ -596,7 +596,7 @@ template <int ARM, int TASK> PIH_D void contacts_warp(const SimParams& P, const 
           dl = fmaxf(dl, -r.lam[0]);
           r.lam[0] += dl;
           float rv = dl * r.diag[0];
-          res_f = fmaxf(res_f, rv * rv);
+          res_f = fmaxf(res_f, fabsf(rv));
           dvl = vaxpy(dl * im, r.dir[0], dvl);
           dvw = vaxpy(dl, r.mang[0], dvw);
         }
@@ -610,12 +610,13 @@ template <int ARM, int TASK> PIH_D void contacts_warp(const SimParams& P, const 
             dl = fminf(fmaxf(dl, -lim - r.lam[d]), lim - r.lam[d]);
             r.lam[d] += dl;
             float rv = dl * r.diag[d];
-            res_f = fmaxf(res_f, rv * rv);
+            res_f = fmaxf(res_f, fabsf(rv));
             dvl = vaxpy(dl * im, r.dir[d], dvl);
             dvw = vaxpy(dl, r.mang[d], dvw);
           }
         }
       }
+      res_f = res_f * res_f;   // (the rows collected max |dv|; rounded squaring is monotone: the oracle's max dv^2 exactly)
       if (res_f <= P.solver_residual) fb_on = false;
       if (!__any_sync(0xffffffffu, fb_on)) break;
     }
