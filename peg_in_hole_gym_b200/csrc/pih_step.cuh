@@ -318,6 +318,96 @@ template <int ARM> struct CRow {
   float dinv[3], diag[3], b[3], lam[3], mu;
 };
 
+// ---- contact rows of one PGS sweep of a warp in which some env couples its islands (finger <-> free body): every lane
+// runs the same straight-line body per row - free-body part, arm part, projection, both updates - with the row's island
+// flag folded into the interval, so the 32 lanes never diverge whatever mix of contact types they hold; values equal
+// the oracle's per-type formulas (rows are zero-filled: the absent terms are exact zeros).  The coefficients of row
+// i + 1 are fetched while row i is being solved (a lone warp otherwise waits for an L1 round trip or three in front of
+// every row); used where the caller can spare two 35-word sets of registers (pih_step_body.inc: kPrefetchRows).
+template <int ARM> struct GRowsIO {
+  float dva[ArmDims<ARM>::NB];
+  v3 dvl, dvw;
+  float res_a, res_f, im, dt;
+  int ncon;
+  bool arm_on, fb_on;
+};
+template <int ARM> struct GRow {
+  v3 dir, jang, mang;
+  float ja[ArmDims<ARM>::NB], ma[ArmDims<ARM>::NB], dinv, b, diag, lam, lam0, mu;
+  int arm_body;
+};
+template <int ARM> PIH_D void grow_load(const CRow<ARM>* rows, int k, int d, GRow<ARM>& R) {
+  const CRow<ARM>& r = rows[k];
+  R.dir = r.dir[d]; R.jang = r.jang[d]; R.mang = r.mang[d];
+#pragma unroll
+  for (int j = 0; j < ArmDims<ARM>::NB; ++j) { R.ja[j] = r.ja[d][j]; R.ma[j] = r.ma[d][j]; }
+  R.dinv = r.dinv[d]; R.b = r.b[d]; R.diag = r.diag[d]; R.lam = r.lam[d]; R.lam0 = r.lam[0]; R.mu = r.mu;
+  R.arm_body = r.arm_body;
+}
+template <int ARM, int TASK> PIH_D void general_rows_sweep(CRow<ARM>* rows, GRowsIO<ARM>& io) {
+  constexpr int nb = ArmDims<ARM>::NB;
+  const int ncon = io.ncon;
+  if (ncon == 0) return;
+  float dva[nb];
+#pragma unroll
+  for (int j = 0; j < nb; ++j) dva[j] = io.dva[j];
+  v3 dvl = io.dvl, dvw = io.dvw;
+  float res_a = io.res_a, res_f = io.res_f;
+  const float im = io.im, dt = io.dt;
+  const bool arm_on = io.arm_on, fb_on = io.fb_on;
+  auto solve = [&](const GRow<ARM>& R, float& lam_out, auto normal_) {
+    constexpr bool NORMAL = decltype(normal_)::value;
+    const bool is_fb = R.arm_body < 0;
+    const bool on = is_fb ? fb_on : arm_on;
+    const float relfb = vdot(R.dir, dvl) + vdot(R.jang, dvw);
+    float s0 = 0.0f, s1 = 0.0f;   // J_arm . dva as two interleaved partial sums (even / odd joints), as in the oracle
+#pragma unroll
+    for (int j = 0; j < nb; j += 2) s0 = fmaf(R.ja[j], dva[j], s0);
+#pragma unroll
+    for (int j = 1; j < nb; j += 2) s1 = fmaf(R.ja[j], dva[j], s1);
+    const float rel = relfb + (s0 + s1);
+    float dl = fmaf(-rel, R.dinv, R.b);
+    const float lam = R.lam;
+    float dlo, dhi;
+    if (NORMAL) { dlo = -lam; dhi = __int_as_float(0x7f800000); }
+    else { const float lim = R.mu * R.lam0; dlo = -lim - lam; dhi = lim - lam; }
+    if (TASK == PIH_TASK_SCRIPTED && R.mu < 0.0f) {   // grasp constraint: bilateral, |impulse| <= maxForce dt
+      const float wl = (float)PIH_GRASP_MAX_FORCE * dt;
+      dlo = -wl - lam; dhi = wl - lam;
+    }
+    dl = fminf(fmaxf(dl, on ? dlo : 0.0f), on ? dhi : 0.0f);
+    lam_out = lam + dl;
+    const float rv = fabsf(dl * R.diag);   // (residuals are collected as |dv| and squared once per sweep by the caller)
+    res_f = fmaxf(res_f, is_fb ? rv : 0.0f);
+    res_a = fmaxf(res_a, is_fb ? 0.0f : rv);
+    dvl = vaxpy(dl * im, R.dir, dvl);
+    dvw = vaxpy(dl, R.mang, dvw);
+#pragma unroll
+    for (int j = 0; j < nb; ++j) dva[j] = fmaf(R.ma[j], dl, dva[j]);
+  };
+  // two sets of coefficients, A and B, used alternately (no copies): while one row is solved the next one loads
+  GRow<ARM> A, B;
+  grow_load<ARM>(rows, 0, 0, A);
+  for (int k = 0; k < ncon; k += 2) {         // normals, in contact order
+    const bool two = k + 1 < ncon;
+    grow_load<ARM>(rows, two ? k + 1 : k, 0, B);
+    solve(A, rows[k].lam[0], std::true_type{});
+    if (!two) break;
+    grow_load<ARM>(rows, k + 2 < ncon ? k + 2 : k + 1, 0, A);
+    solve(B, rows[k + 1].lam[0], std::true_type{});
+  }
+  grow_load<ARM>(rows, 0, 1, A);              // (after the normals: a friction row's interval is mu * its normal impulse)
+  for (int k = 0; k < ncon; ++k) {            // friction rows: directions 1 and 2 of contact k
+    grow_load<ARM>(rows, k, 2, B);
+    solve(A, rows[k].lam[1], std::false_type{});
+    grow_load<ARM>(rows, k + 1 < ncon ? k + 1 : k, 1, A);
+    solve(B, rows[k].lam[2], std::false_type{});
+  }
+#pragma unroll
+  for (int j = 0; j < nb; ++j) io.dva[j] = dva[j];
+  io.dvl = dvl; io.dvw = dvw; io.res_a = res_a; io.res_f = res_f;
+}
+
 template <int ARM> PIH_D unsigned anc_rt(int body) {
   unsigned a = 0;
 #pragma unroll
