@@ -645,11 +645,18 @@ template <int ARM, int TASK> PIH_D void contacts_warp(const SimParams& P, const 
     Iinv = mmulT(Tm, Rfb);
   }
   ContactSet CS;
-  collide<ARM, TASK, 3>(P, S, F, Rfb, fsm_state_now<TASK>(S, false), CS);
+  CS.n = 0;
+  // Scripted task: while the grasp constraint is on in some env of the warp (states 4..6; the state machine is
+  // time-driven, so normally in all of them) that env has a row on the arm - the constraint itself - and the dynamics
+  // warp will run the narrow phase and build every row anyway: skip the narrow phase here, so that this warp's M^-1
+  // columns are ready as soon as the factorisation is and the dynamics warp does not wait for a result it discards.
+  bool w_grasp = false;
+  if constexpr (TASK == PIH_TASK_SCRIPTED) w_grasp = __any_sync(0xffffffffu, grasp_active(TASK, fsm_state_now<TASK>(S, false)));
+  if (!w_grasp) collide<ARM, TASK, 3>(P, S, F, Rfb, fsm_state_now<TASK>(S, false), CS);
   int pairmask = 0;
   bool arm_contacts = false;
   for (int k = 0; k < CS.n; ++k) { pairmask |= CS.c[k].pair; arm_contacts = arm_contacts || (CS.c[k].arm_body >= 0); }
-  const bool w_armc = __any_sync(0xffffffffu, arm_contacts);
+  const bool w_armc = w_grasp || __any_sync(0xffffffffu, arm_contacts);
   v3 dvl = mk(0.0f, 0.0f, 0.0f), dvw = dvl;
   int st_rowit = 0, st_it = 0;
   if (!w_armc) {
