@@ -497,6 +497,25 @@ def test_scripted_grasp_fsm_bit_exact_and_through_gym_surface():
     env.close()
 
 
+@pytest.mark.parametrize("family", ["ws", "ws2", "fused"])
+def test_scripted_episode_bit_exact_in_every_kernel_family(family):
+    """The scripted episode through its grasp and lift phases (grasp constraint + finger contacts in every env: the
+    coupled contact rows, which the scripted small-batch kernels solve from two alternating sets of coefficients with
+    M^-1 in shared memory, and the contacts warp's narrow-phase skip) in the three-warp, the two-warp and the fused
+    kernel, against the oracle bit for bit.  100 envs: padding lanes in the last CTA."""
+    from peg_in_hole_gym_b200.sim import BatchedSim
+    n = 100
+    sim = BatchedSim(n, task="peg-in-hole-scripted", offset=(2.0, 3.0, 0.0), seed=11, device=0, kernel_family=family)
+    orc = ol.Oracle(ol.make_config(n, task=2, offset=(2.0, 3.0, 0.0), seed=11))
+    assert np.array_equal(sim.reset().cpu().numpy(), orc.reset())
+    for chunk in (1100, 300, 400, 426):                  # approach + close | grasp on | lift | carry, insert, release
+        sim.rollout(chunk)
+        orc.rollout(chunk)
+        _assert_state_equal(sim, orc)
+    assert sim.done.cpu().numpy().all() and np.array_equal(sim.reward.cpu().numpy(), orc.reward)
+    sim.close()
+
+
 def test_camera_render_matches_oracle_and_full_size():
     """PegInHole.render as a batched ray caster; CUDA image == oracle image, then 300x300."""
     from peg_in_hole_gym_b200.sim import BatchedSim
