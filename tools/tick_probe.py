@@ -44,7 +44,7 @@ for t in range(steps):
     torch.cuda.synchronize()
     tot += ev0.elapsed_time(ev1)
     L.pih_debug_ticks(buf)
-    rows.append(list(buf)[:9])
+    rows.append(list(buf)[:16])
     L.pih_debug_cta_ns(cta)
     ctas.append(np.array(list(cta)[:2 * ((n + 31) // 32)], dtype=np.float64).reshape(-1, 2))
     if t in (180, 190):
@@ -69,6 +69,8 @@ def us(a, b):
 print(f"n={n}: event mean {1e3 * tot / steps:.1f} us/step (with a sync after every step)")
 print(f"warp0  FK+apply_action(IK)         {us(0, 1):6.1f} us")
 print(f"warp1  FK+ABA+Minv+collide+rows    {us(2, 3):6.1f} us")
+print(f"warp1    of which FK+ABA+publish     {us(2, 12):6.1f} us, own M^-1 columns + free-body setup {us(12, 13):6.1f} us, waits + narrow phase + rows {us(13, 3):6.1f} us")
+print(f"warp2  start -> contact summary    {us(9, 10):6.1f} us, -> its M^-1 columns done {us(9, 11):6.1f} us (after warp 1's start: {us(2, 11):6.1f} us)")
 print(f"warp1  barrier+motor/limit setup   {us(3, 4):6.1f} us")
 print(f"warp1  PGS                         {us(4, 5):6.1f} us")
 print(f"warp1  integrate+FK+get_info       {us(5, 7):6.1f} us")
