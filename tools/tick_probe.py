@@ -82,6 +82,9 @@ span = (c[:, :, 1].max(1) - c[:, :, 0].min(1)) / 1e3
 print(f"per-CTA duration (globaltimer): median {np.median(dur):.1f} us, p90 {np.percentile(dur, 90):.1f}, max-per-step median {np.median(dur.max(1)):.1f}; "
       f"first-start to last-end median {np.median(span):.1f} us; start skew median {np.median((c[:, :, 0].max(1) - c[:, :, 0].min(1)) / 1e3):.1f} us")
 
+mx = dur.max(1)
+print(f"slowest CTA per step: mean {mx.mean():.1f} us, median {np.median(mx):.1f}, p90 {np.percentile(mx, 90):.1f}; steps whose slowest CTA takes > 1.15 x the median CTA: "
+      f"{float((mx > 1.15 * np.median(dur)).mean()):.2f}; CTAs over that bar per step: {float((dur > 1.15 * np.median(dur)).sum(1).mean()):.2f} of {dur.shape[1]}")
 # per 25-step block of the episode (all envs of the batch share the phase): where does the time go?
 print("block  IK    prologue  setup  PGS   tail   total(us)")
 for b0 in range(0, steps, 25):
